@@ -1,0 +1,275 @@
+/*
+ * soket_b200.h -- C ABI of libsoketb200.so, the B200 (sm_100a) device backend
+ * that sits where CuPy sits in singul4ri7y/soket.
+ *
+ * Every entry point takes plain pointers / sizes / small POD structs, returns
+ * an int status (SK_OK == 0) and never throws.  On failure the message is
+ * available from sk_last_error().  All launches go to ONE per-process stream
+ * (sk_stream()), are asynchronous, and surface execution errors at the next
+ * sk_sync()/sk_d2h().  The library never frees caller memory and never keeps
+ * a caller pointer past the call.  Single-threaded use (the reference holds the
+ * GIL and is not thread-safe: soket/backend/device.pyx:261, tensor.pyx:24).
+ *
+ * "replaces:" comments cite the reference interface (file:line under the
+ * soket tree) that each entry point stands in for.
+ */
+#ifndef SOKET_B200_H
+#define SOKET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_OK 0
+#define SK_ERR_CUDA 1
+#define SK_ERR_ARG 2
+#define SK_ERR_UNSUPPORTED 3
+#define SK_ERR_NCCL 4
+#define SK_ERR_OOM 5
+
+#define SK_MAX_NDIM 8
+
+/* dtype tags: same 12 names as soket/dtype.pyx:12-14, plus bf16 (GEMM input only). */
+typedef enum {
+  SK_BOOL = 0,
+  SK_I8 = 1,
+  SK_U8 = 2,
+  SK_I16 = 3,
+  SK_U16 = 4,
+  SK_I32 = 5,
+  SK_U32 = 6,
+  SK_I64 = 7,
+  SK_U64 = 8,
+  SK_F16 = 9,
+  SK_F32 = 10,
+  SK_F64 = 11,
+  SK_BF16 = 12
+} sk_dtype;
+
+/* Strided view of device memory.  `data` points at element [0,...,0];
+ * strides are in ELEMENTS (may be 0 = broadcast, or negative). */
+typedef struct {
+  void *data;
+  int32_t dtype;
+  int32_t ndim;
+  int64_t shape[SK_MAX_NDIM];
+  int64_t strides[SK_MAX_NDIM];
+} sk_array;
+
+/* ------------------------------------------------------------------ runtime
+ * replaces: cupy.cuda.Device(id).use()/synchronize() as called from
+ * soket/backend/device.pyx:56-58,188-198; cupy's memory pool; cupy.asnumpy /
+ * cupy.array H2D-D2H (soket/tensor/tensor.pyx:384-442). */
+int sk_init(int device);
+int sk_device_count(int *count);
+int sk_current_device(int *device);
+int sk_sync(void);
+const char *sk_last_error(void);
+const char *sk_version(void);
+void *sk_stream(void); /* cudaStream_t of the compute stream */
+
+int sk_malloc(size_t nbytes, void **ptr); /* stream-ordered caching allocator */
+int sk_free(void *ptr);
+int sk_empty_cache(void);
+int sk_mem_stats(size_t *in_use, size_t *reserved, size_t *peak_in_use);
+int sk_host_alloc(size_t nbytes, void **ptr); /* pinned host memory */
+int sk_host_free(void *ptr);
+int sk_h2d(void *dst, const void *src, size_t nbytes);       /* sync on return */
+int sk_d2h(void *dst, const void *src, size_t nbytes);       /* sync on return */
+int sk_h2d_async(void *dst, const void *src, size_t nbytes); /* src must be pinned */
+int sk_d2h_async(void *dst, const void *src, size_t nbytes); /* dst must be pinned */
+int sk_d2d(void *dst, const void *src, size_t nbytes);
+int sk_memset(void *dst, int byte, size_t nbytes);
+
+/* timing + launch accounting (bench.py: CUDA events on the launching stream) */
+int sk_event_create(void **ev);
+int sk_event_record(void *ev);
+int sk_event_sync(void *ev);
+int sk_event_elapsed_ms(void *start, void *stop, float *ms);
+int sk_event_destroy(void *ev);
+uint64_t sk_launch_count(void); /* kernels this library launched so far */
+int sk_flush_l2(void);          /* overwrite a >L2 scratch buffer */
+
+/* CUDA-graph capture of a static-shape step */
+int sk_graph_begin(void);
+int sk_graph_end(void **graph_exec);
+int sk_graph_launch(void *graph_exec);
+int sk_graph_destroy(void *graph_exec);
+
+/* ------------------------------------------------------- elementwise family
+ * replaces: intern-table slots _ADD.._POW, _NEG, _MAXIMUM, _EXP, _LOG,
+ * _EQUAL.._LESS_EQUAL, _ARRAY/_COPY, _BCASTTO/_TRANSPOSE/_RESHAPE when they
+ * must be materialised (soket/tensor/ops/intern.pyx:45-76; call shapes in
+ * soket/tensor/ops/forward.pyx:7-221). NumPy broadcasting is expressed by the
+ * caller through zero strides; `out` is written in its own dtype. */
+typedef enum {
+  SK_OP_ADD = 0,
+  SK_OP_SUB = 1,
+  SK_OP_MUL = 2,
+  SK_OP_DIV = 3,
+  SK_OP_POW = 4,
+  SK_OP_MAXIMUM = 5,
+  SK_OP_MINIMUM = 6,
+  /* comparisons: out dtype bool */
+  SK_OP_EQ = 16,
+  SK_OP_NE = 17,
+  SK_OP_GT = 18,
+  SK_OP_GE = 19,
+  SK_OP_LT = 20,
+  SK_OP_LE = 21
+} sk_binary_op;
+
+typedef enum {
+  SK_UOP_NEG = 0,
+  SK_UOP_EXP = 1,
+  SK_UOP_LOG = 2,
+  SK_UOP_SQRT = 3,
+  SK_UOP_RELU = 4, /* maximum(x, 0) fast path: forward.pyx:206-209 */
+  SK_UOP_ABS = 5
+} sk_unary_op;
+
+/* out = a (op) b ; a, b, out share shape (broadcast dims have stride 0). */
+int sk_ewise_binary(int op, const sk_array *a, const sk_array *b, sk_array *out);
+/* out = a (op) s, or s (op) a when reverse != 0.  The scalar is a weak Python
+ * scalar (NEP 50): it adopts the array's kind, so it is passed as a double and
+ * an int64 (scalar_is_int selects). */
+int sk_ewise_scalar(int op, const sk_array *a, double fscalar, int64_t iscalar,
+                    int scalar_is_int, int reverse, sk_array *out);
+int sk_ewise_unary(int op, const sk_array *a, sk_array *out);
+/* dst[...] = cast(src[...]) for arbitrary strides on both sides: compaction,
+ * astype, broadcast materialisation, slice __setitem__ (tensor.pyx:948). */
+int sk_copy(const sk_array *src, sk_array *dst);
+int sk_fill(sk_array *dst, double fvalue, int64_t ivalue, int value_is_int);
+/* relu backward: out = (x > 0) * adj  (backward.pyx:849-874) in one pass */
+int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out);
+
+/* ---------------------------------------------------------------- reductions
+ * replaces: _SUM/_MEAN/_MAX/_MIN/_ARGMAX/_ARGMIN (intern.pyx:52-57), call
+ * convention f(x, axes, dtype, out, keepdims) (forward.pyx:128-170).
+ * `axes_mask` bit i set => axis i of `in` is reduced.  `out` is the contiguous
+ * result WITHOUT the reduced axes (keepdims is a host-side reshape). */
+typedef enum { SK_RED_SUM = 0, SK_RED_MEAN = 1, SK_RED_MAX = 2, SK_RED_MIN = 3 } sk_reduce_op;
+int sk_reduce(int op, const sk_array *in, uint32_t axes_mask, sk_array *out);
+/* axis < 0: over the flattened array.  out dtype int64 (NumPy) or int32. */
+int sk_argreduce(int is_min, const sk_array *in, int axis, sk_array *out);
+
+/* ------------------------------------------------------------------ indexing
+ * replaces: ndarray.__getitem__ with an integer array (device.pyx:236-239,
+ * `eye(C)[labels]`), eye (device.pyx:69), np.stack (util.pyx:36). */
+int sk_gather_rows(const sk_array *src, const sk_array *index, sk_array *out);
+int sk_eye(sk_array *out, int64_t k);
+int sk_one_hot(const sk_array *labels, sk_array *out); /* out[b, labels[b]] = 1 else 0 */
+
+/* ----------------------------------------------------------------------- RNG
+ * replaces: cupy.random.uniform/normal/binomial(1,p) (device.pyx:64-66,
+ * 204-224).  Philox4x32-10, counter-based; stream = (seed, offset). */
+int sk_rng_seed(uint64_t seed);
+int sk_rng_uniform(sk_array *out, double low, double high);
+int sk_rng_normal(sk_array *out, double mean, double std);
+int sk_rng_bernoulli(sk_array *out, double p);
+
+/* -------------------------------------------------------------------- matmul
+ * replaces: _MATMUL (intern.pyx:63): np.matmul(x, y, dtype='float32') with
+ * row-major or transposed (.T view) 2-D operands (forward.pyx:172-178,
+ * backward.pyx:704-742) and leading batch dims.
+ * a: (..., M, K)   b: (..., K, N)   out: (..., M, N) contiguous fp32.
+ * Operand strides select K-major / MN-major in the tensor-core path; anything
+ * else is compacted by the caller first.
+ *   SK_MM_AUTO      tcgen05 3xTF32 when shapes allow, else SIMT fp32
+ *   SK_MM_SIMT      CUDA-core fp32 FFMA (exact fp32 products; validation path)
+ *   SK_MM_TF32X3    tcgen05 kind::tf32, error-compensated hi/lo split
+ *   SK_MM_TF32      tcgen05 kind::tf32 single pass (1e-3 class; not parity)
+ *   SK_MM_BF16      tcgen05 kind::f16 on bf16 operands (a,b dtype SK_BF16) */
+typedef enum { SK_MM_AUTO = 0, SK_MM_SIMT = 1, SK_MM_TF32X3 = 2, SK_MM_TF32 = 3, SK_MM_BF16 = 4 } sk_mm_algo;
+typedef enum {
+  SK_EPI_NONE = 0,
+  SK_EPI_BIAS = 1,      /* + bias[n]                (prototypes.pyx:108-115) */
+  SK_EPI_BIAS_RELU = 2, /* relu(. + bias[n])        (+ prototypes.pyx:302)   */
+  SK_EPI_RELU = 3
+} sk_mm_epilogue;
+int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo);
+/* fused Linear(+ReLU): out = epi(x @ w + bias). bias may be NULL for EPI_NONE/RELU */
+int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
+                  sk_array *out, int epilogue, int algo);
+/* fp32 -> bf16 (RNE) cast for the bf16 sweep */
+int sk_cast_bf16(const sk_array *src, sk_array *dst);
+
+/* ------------------------------------------------------------ fused nn kernels
+ * replaces the op SEQUENCES of forward.pyx:224-353 / backward.pyx:959-1132. */
+/* LayerNorm over the last axis of a contiguous (rows, cols) fp32 matrix.
+ * y = gamma * ((x-mean) * rstd) + beta ; biased variance ; saves mean/rstd.
+ * relu != 0 fuses the following ReLU; residual != NULL fuses
+ * relu(residual + LN(x)) (model.py:34-37, prototypes.pyx:272-273). */
+int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta,
+                     const float *residual, float *y, float *mean, float *rstd,
+                     int64_t rows, int64_t cols, float eps, int relu);
+/* dX, dgamma, dbeta (per-group partials column-reduced internally).
+ * mask_mode: 0 none; 1 the LN output fed a ReLU directly: the mask (LN(x) > 0)
+ * is recomputed from x/mean/rstd/gamma/beta, nothing extra is read; 2 the mask
+ * is (y_out > 0) for the fused relu(residual + LN(x)) output.  dresidual (may be
+ * NULL) receives the masked adjoint = gradient of the residual branch.
+ * Quirk kept: dgamma/dbeta are summed over axis 0 (backward.pyx:1052-1055). */
+int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                     const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                     float *dx, float *dgamma, float *dbeta, float *dresidual,
+                     int64_t rows, int64_t cols);
+/* BatchNorm1d over axis 0 of a contiguous (rows, cols) fp32 matrix, training
+ * mode (always: quirk Q4, forward.pyx:281), biased variance, running stats
+ * rm = (1-m) rm + m mean (forward.pyx:308-318). */
+int sk_batchnorm_fwd(const float *x, const float *gamma, const float *beta,
+                     float *y, float *mean, float *rstd, float *running_mean,
+                     float *running_var, int64_t rows, int64_t cols, float eps,
+                     float momentum, int relu);
+int sk_batchnorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                     const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                     float *dx, float *dgamma, float *dbeta, int64_t rows, int64_t cols);
+/* softmax cross-entropy, mean reduction, integer labels (no one-hot):
+ * loss = mean_b(logsumexp(x_b) - x_b[y_b]) ; dx = (softmax(x) - onehot) / B.
+ * labels dtype u8/i32/i64.  (forward.pyx:250-271, backward.pyx:959-1022) */
+int sk_softmax_ce_fwd_bwd(const float *logits, const void *labels, int label_dtype,
+                          float *loss, float *dlogits, float *row_loss,
+                          int64_t rows, int64_t classes);
+/* out = relu(a + b)  (Residual + outer ReLU) */
+int sk_add_relu(const float *a, const float *b, float *out, int64_t n);
+/* dropout: out = x * mask * (1/keep), mask ~ Bernoulli(keep) written as fp32 */
+int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float keep);
+/* bias gradient: out[c] = sum_r adj[r, c]  (autodiff.pyx:43-101) ;
+ * y_out != NULL applies the relu mask first. */
+int sk_colsum(const float *adj, const float *y_out, float *out, int64_t rows, int64_t cols);
+/* grad accumulation in place: acc += part (autodiff.pyx:30-41) */
+int sk_accumulate(float *acc, const float *part, int64_t n);
+
+/* ------------------------------------------------------------------ optimizers
+ * replaces: SGD.step (optim.pyx:82-131) and Adam.step (optim.pyx:201-269):
+ * ONE launch over all parameter tensors (HOST arrays of device pointers; up to
+ * 48 tensors per launch).  Hyper-parameters arrive as the Python doubles the
+ * reference holds and are rounded to float32 exactly where NumPy would (NEP 50).  grad_scale folds the 1/W
+ * of data-parallel averaging.  Arithmetic order follows the reference
+ * including quirks Q2/Q3. */
+int sk_sgd_step(int n_tensors, float *const *params, const float *const *grads,
+                const int64_t *sizes, double lr, double weight_decay, double grad_scale);
+int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
+                 float *const *m, float *const *v, const int64_t *sizes, double lr,
+                 double beta1, double beta2, double eps, double weight_decay,
+                 double one_minus_beta1_t, double one_minus_beta2_t, int first_step,
+                 double grad_scale);
+
+/* ------------------------------------------------------------- data parallel
+ * new (the reference has no collective): NCCL all-reduce(sum) of fp32
+ * gradient buckets on a dedicated comm stream. */
+#define SK_NCCL_ID_BYTES 128
+int sk_nccl_available(void);
+int sk_nccl_unique_id(char id[SK_NCCL_ID_BYTES]);
+int sk_nccl_init(int rank, int world, const char id[SK_NCCL_ID_BYTES]);
+int sk_nccl_allreduce(float *buf, size_t count, int on_comm_stream);
+int sk_nccl_broadcast(float *buf, size_t count, int root);
+int sk_nccl_wait(void); /* compute stream waits for the comm stream */
+int sk_nccl_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOKET_B200_H */

@@ -1,0 +1,78 @@
+"""oracle/ref_model.py -- drive the BUILT reference (oracle/_ref) as an oracle.
+
+TEST INFRASTRUCTURE ONLY.  Builds the north-star model of
+examples/mlp_resnet/model.py:17-58 out of the reference's own ``soket.nn``
+modules (or any API-compatible ``nn`` namespace, e.g. ``soket_b200.engine.nn``),
+in the `self.fn`-retaining variant that makes the inner layers visible to
+``parameters()`` / ``modules()``, and maps parameters to the
+flat names used by ``oracle/soket_np.py``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def import_reference():
+    """Import the built reference package; returns the `soket` module or None."""
+    if not os.path.exists(os.path.join(REF_DIR, "soket", "__init__.py")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import soket  # noqa: F401
+    return soket
+
+
+def build_model(nn, dim, hidden, num_blocks, num_classes, norm="layer", drop_prob=0.0, retain_fn=True):
+    """Same composition as model.py:17-58.  `retain_fn=False` is the verbatim model
+    (inner layers invisible to parameters(): quirk Q1)."""
+    norm_cls = nn.LayerNorm if norm == "layer" else nn.BatchNorm1d
+
+    class ResidualBlock(nn.Sequential):
+        def __init__(self, d, h):
+            fn = nn.Sequential(
+                nn.Linear(d, h), norm_cls(h), nn.ReLU(), nn.Dropout(p=drop_prob),
+                nn.Linear(h, h), norm_cls(h))
+            super().__init__(nn.Residual(fn), nn.ReLU())
+            if retain_fn:
+                self.fn = fn
+
+    class MLPResNet(nn.Sequential):
+        def __init__(self):
+            blocks = [ResidualBlock(hidden, hidden) for _ in range(num_blocks)]
+            super().__init__(nn.Linear(dim, hidden), nn.ReLU(), *blocks, nn.Linear(hidden, num_classes))
+
+    return MLPResNet()
+
+
+def named_parameters(model, num_blocks):
+    """Flat name -> Tensor, names as in oracle.soket_np.MLPResNet (needs retain_fn)."""
+    mods = list(model.modules())
+    lin0 = None
+    out = {}
+    # model._storage order: Linear, ReLU, blocks..., Linear -- reach them via modules()
+    linears = [m for m in mods if type(m).__name__ == "Linear"]
+    norms = [m for m in mods if type(m).__name__ in ("LayerNorm", "BatchNorm1d")]
+    # modules() walks the model's storage in order; each block exposes its inner
+    # layers through its `fn` attribute: lin0, blk0.lin1, blk0.lin2, ..., out
+    assert len(linears) == 2 + 2 * num_blocks, len(linears)
+    lin0, last = linears[0], linears[-1]
+    inner = linears[1:-1]
+    out["lin0.W"], out["lin0.b"] = lin0.weight, lin0.bias
+    for i in range(num_blocks):
+        l1, l2 = inner[2 * i], inner[2 * i + 1]
+        n1, n2 = norms[2 * i], norms[2 * i + 1]
+        out[f"blk{i}.lin1.W"], out[f"blk{i}.lin1.b"] = l1.weight, l1.bias
+        g1, b1 = list(n1.parameters())
+        out[f"blk{i}.n1.g"], out[f"blk{i}.n1.b"] = g1, b1
+        out[f"blk{i}.lin2.W"], out[f"blk{i}.lin2.b"] = l2.weight, l2.bias
+        g2, b2 = list(n2.parameters())
+        out[f"blk{i}.n2.g"], out[f"blk{i}.n2.b"] = g2, b2
+    out["out.W"], out["out.b"] = last.weight, last.bias
+    return out

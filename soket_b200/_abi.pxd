@@ -1,0 +1,162 @@
+# _abi.pxd -- Cython view of include/soket_b200.h (the C-ABI of libsoketb200.so).
+from libc.stdint cimport int32_t, int64_t, uint32_t, uint64_t
+
+cdef extern from "soket_b200.h" nogil:
+    enum: SK_OK
+    enum: SK_MAX_NDIM
+    enum: SK_NCCL_ID_BYTES
+
+    enum: SK_BOOL
+    enum: SK_I8
+    enum: SK_U8
+    enum: SK_I16
+    enum: SK_U16
+    enum: SK_I32
+    enum: SK_U32
+    enum: SK_I64
+    enum: SK_U64
+    enum: SK_F16
+    enum: SK_F32
+    enum: SK_F64
+    enum: SK_BF16
+
+    enum: SK_OP_ADD
+    enum: SK_OP_SUB
+    enum: SK_OP_MUL
+    enum: SK_OP_DIV
+    enum: SK_OP_POW
+    enum: SK_OP_MAXIMUM
+    enum: SK_OP_MINIMUM
+    enum: SK_OP_EQ
+    enum: SK_OP_NE
+    enum: SK_OP_GT
+    enum: SK_OP_GE
+    enum: SK_OP_LT
+    enum: SK_OP_LE
+
+    enum: SK_UOP_NEG
+    enum: SK_UOP_EXP
+    enum: SK_UOP_LOG
+    enum: SK_UOP_SQRT
+    enum: SK_UOP_RELU
+    enum: SK_UOP_ABS
+
+    enum: SK_RED_SUM
+    enum: SK_RED_MEAN
+    enum: SK_RED_MAX
+    enum: SK_RED_MIN
+
+    enum: SK_MM_AUTO
+    enum: SK_MM_SIMT
+    enum: SK_MM_TF32X3
+    enum: SK_MM_TF32
+    enum: SK_MM_BF16
+
+    enum: SK_EPI_NONE
+    enum: SK_EPI_BIAS
+    enum: SK_EPI_BIAS_RELU
+    enum: SK_EPI_RELU
+
+    ctypedef struct sk_array:
+        void *data
+        int32_t dtype
+        int32_t ndim
+        int64_t shape[8]
+        int64_t strides[8]
+
+    int sk_init(int device)
+    int sk_device_count(int *count)
+    int sk_current_device(int *device)
+    int sk_sync()
+    const char *sk_last_error()
+    const char *sk_version()
+    void *sk_stream()
+
+    int sk_malloc(size_t nbytes, void **ptr)
+    int sk_free(void *ptr)
+    int sk_empty_cache()
+    int sk_mem_stats(size_t *in_use, size_t *reserved, size_t *peak_in_use)
+    int sk_host_alloc(size_t nbytes, void **ptr)
+    int sk_host_free(void *ptr)
+    int sk_h2d(void *dst, const void *src, size_t nbytes)
+    int sk_d2h(void *dst, const void *src, size_t nbytes)
+    int sk_h2d_async(void *dst, const void *src, size_t nbytes)
+    int sk_d2h_async(void *dst, const void *src, size_t nbytes)
+    int sk_d2d(void *dst, const void *src, size_t nbytes)
+    int sk_memset(void *dst, int byte, size_t nbytes)
+
+    int sk_event_create(void **ev)
+    int sk_event_record(void *ev)
+    int sk_event_sync(void *ev)
+    int sk_event_elapsed_ms(void *start, void *stop, float *ms)
+    int sk_event_destroy(void *ev)
+    uint64_t sk_launch_count()
+    int sk_flush_l2()
+
+    int sk_graph_begin()
+    int sk_graph_end(void **graph_exec)
+    int sk_graph_launch(void *graph_exec)
+    int sk_graph_destroy(void *graph_exec)
+
+    int sk_ewise_binary(int op, const sk_array *a, const sk_array *b, sk_array *out)
+    int sk_ewise_scalar(int op, const sk_array *a, double fscalar, int64_t iscalar,
+                        int scalar_is_int, int reverse, sk_array *out)
+    int sk_ewise_unary(int op, const sk_array *a, sk_array *out)
+    int sk_copy(const sk_array *src, sk_array *dst)
+    int sk_fill(sk_array *dst, double fvalue, int64_t ivalue, int value_is_int)
+    int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out)
+
+    int sk_reduce(int op, const sk_array *inp, uint32_t axes_mask, sk_array *out)
+    int sk_argreduce(int is_min, const sk_array *inp, int axis, sk_array *out)
+
+    int sk_gather_rows(const sk_array *src, const sk_array *index, sk_array *out)
+    int sk_eye(sk_array *out, int64_t k)
+    int sk_one_hot(const sk_array *labels, sk_array *out)
+
+    int sk_rng_seed(uint64_t seed)
+    int sk_rng_uniform(sk_array *out, double low, double high)
+    int sk_rng_normal(sk_array *out, double mean, double std)
+    int sk_rng_bernoulli(sk_array *out, double p)
+
+    int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo)
+    int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
+                      sk_array *out, int epilogue, int algo)
+    int sk_cast_bf16(const sk_array *src, sk_array *dst)
+
+    int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta,
+                         const float *residual, float *y, float *mean, float *rstd,
+                         int64_t rows, int64_t cols, float eps, int relu)
+    int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                         const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                         float *dx, float *dgamma, float *dbeta, float *dresidual,
+                         int64_t rows, int64_t cols)
+    int sk_batchnorm_fwd(const float *x, const float *gamma, const float *beta,
+                         float *y, float *mean, float *rstd, float *running_mean,
+                         float *running_var, int64_t rows, int64_t cols, float eps,
+                         float momentum, int relu)
+    int sk_batchnorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                         const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                         float *dx, float *dgamma, float *dbeta, int64_t rows, int64_t cols)
+    int sk_softmax_ce_fwd_bwd(const float *logits, const void *labels, int label_dtype,
+                              float *loss, float *dlogits, float *row_loss,
+                              int64_t rows, int64_t classes)
+    int sk_add_relu(const float *a, const float *b, float *out, int64_t n)
+    int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float keep)
+    int sk_colsum(const float *adj, const float *y_out, float *out, int64_t rows, int64_t cols)
+    int sk_accumulate(float *acc, const float *part, int64_t n)
+
+    int sk_sgd_step(int n_tensors, float *const *params, const float *const *grads,
+                    const int64_t *sizes, double lr, double weight_decay, double grad_scale)
+    int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
+                     float *const *m, float *const *v, const int64_t *sizes, double lr,
+                     double beta1, double beta2, double eps, double weight_decay,
+                     double one_minus_beta1_t, double one_minus_beta2_t, int first_step,
+                     double grad_scale)
+
+    int sk_nccl_available()
+    int sk_nccl_unique_id(char *id)
+    int sk_nccl_init(int rank, int world, const char *id)
+    int sk_nccl_allreduce(float *buf, size_t count, int on_comm_stream)
+    int sk_nccl_broadcast(float *buf, size_t count, int root)
+    int sk_nccl_wait()
+    int sk_nccl_destroy()

@@ -1,0 +1,139 @@
+// matmul.cu -- sk_matmul / sk_linear_fwd dispatch.
+// Replaces _MATMUL (soket/tensor/ops/intern.pyx:63) as called from
+// forward.pyx:172-178 (x @ y) and backward.pyx:704-742 (adj @ y.T, x.T @ adj),
+// and the Linear(+ReLU) module sequence prototypes.pyx:108-115,302.
+#include "common.cuh"
+#include "matmul.cuh"
+
+namespace sk {
+
+static int parse_2d(const sk_array *a, const sk_array *b, const sk_array *out, GemmProblem &g) {
+  SK_REQUIRE(a && b && out, "matmul: null array");
+  SK_REQUIRE(a->ndim >= 2 && b->ndim >= 2, "matmul: operands must be at least 2-D");
+  SK_REQUIRE(out->ndim >= 2 && out->ndim >= a->ndim && out->ndim >= b->ndim, "matmul: bad output rank");
+  g.M = a->shape[a->ndim - 2];
+  g.K = a->shape[a->ndim - 1];
+  g.N = b->shape[b->ndim - 1];
+  SK_REQUIRE(b->shape[b->ndim - 2] == g.K, "matmul: inner dimensions differ (%lld vs %lld)",
+             (long long)g.K, (long long)b->shape[b->ndim - 2]);
+  SK_REQUIRE(out->shape[out->ndim - 2] == g.M && out->shape[out->ndim - 1] == g.N,
+             "matmul: output shape mismatch");
+  SK_REQUIRE(out->dtype == SK_F32, "matmul: output must be float32");
+  SK_REQUIRE(out->strides[out->ndim - 1] == 1 || g.N == 1, "matmul: output rows must be contiguous");
+  g.sa_m = a->strides[a->ndim - 2];
+  g.sa_k = a->strides[a->ndim - 1];
+  g.sb_k = b->strides[b->ndim - 2];
+  g.sb_n = b->strides[b->ndim - 1];
+  g.ldc = g.M > 1 ? out->strides[out->ndim - 2] : g.N;
+  return SK_OK;
+}
+
+static int run_one(const GemmProblem &g0, int algo) {
+  GemmProblem g = g0;
+  if (g.M == 0 || g.N == 0 || g.batch == 0) return SK_OK;
+  if (g.K == 0) {
+    // empty inner dimension: result is epilogue(0)
+    set_error("matmul: K == 0 is not supported");
+    return SK_ERR_UNSUPPORTED;
+  }
+  if (g.a_dtype == SK_BF16 || g.b_dtype == SK_BF16) {
+    SK_REQUIRE(g.a_dtype == SK_BF16 && g.b_dtype == SK_BF16, "matmul: mixed bf16/fp32 operands");
+    SK_REQUIRE(algo == SK_MM_AUTO || algo == SK_MM_BF16, "matmul: bf16 operands need SK_MM_BF16");
+    if (!tc_supported(g, SK_MM_BF16)) {
+      set_error("matmul(bf16): shape/strides not supported by the tcgen05 path (M=%lld N=%lld K=%lld)",
+                (long long)g.M, (long long)g.N, (long long)g.K);
+      return SK_ERR_UNSUPPORTED;
+    }
+    return launch_gemm_tc(g, SK_MM_BF16);
+  }
+  SK_REQUIRE(g.a_dtype == SK_F32 && g.b_dtype == SK_F32, "matmul: operands must be float32 (or bf16)");
+  if (algo == SK_MM_AUTO) algo = tc_supported(g, SK_MM_TF32X3) && tc_profitable(g) ? SK_MM_TF32X3 : SK_MM_SIMT;
+  if (algo == SK_MM_SIMT) {
+    MMArgs p;
+    p.a = (const float *)g.a; p.b = (const float *)g.b; p.c = g.c; p.bias = g.bias;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.sa_m = g.sa_m; p.sa_k = g.sa_k; p.sb_k = g.sb_k; p.sb_n = g.sb_n; p.ldc = g.ldc;
+    p.batch = g.batch; p.sa_b = g.sa_b; p.sb_b = g.sb_b; p.sc_b = g.sc_b;
+    p.epilogue = g.epilogue;
+    return launch_gemm_simt(p);
+  }
+  if (!tc_supported(g, algo)) {
+    set_error("matmul: tcgen05 path does not support this problem (M=%lld N=%lld K=%lld, strides a(%lld,%lld) b(%lld,%lld))",
+              (long long)g.M, (long long)g.N, (long long)g.K, (long long)g.sa_m, (long long)g.sa_k,
+              (long long)g.sb_k, (long long)g.sb_n);
+    return SK_ERR_UNSUPPORTED;
+  }
+  return launch_gemm_tc(g, algo);
+}
+
+static int matmul_impl(const sk_array *a, const sk_array *b, const sk_array *bias, sk_array *out,
+                       int epilogue, int algo) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  if ((rc = parse_2d(a, b, out, g))) return rc;
+  g.a = a->data; g.b = b->data; g.c = (float *)out->data;
+  g.a_dtype = a->dtype; g.b_dtype = b->dtype;
+  g.epilogue = epilogue;
+  if (epilogue == SK_EPI_BIAS || epilogue == SK_EPI_BIAS_RELU) {
+    SK_REQUIRE(bias && bias->dtype == SK_F32 && numel(bias) == g.N &&
+                   (g.N == 1 || bias->strides[bias->ndim - 1] == 1),
+               "linear: bias must be a contiguous float32 vector of length N");
+    g.bias = (const float *)bias->data;
+  }
+  // leading (batch) dims: broadcast operands against out's leading dims
+  const int nb = out->ndim - 2;
+  int64_t bshape[SK_MAX_NDIM], sa[SK_MAX_NDIM], sb[SK_MAX_NDIM], sc[SK_MAX_NDIM];
+  for (int i = 0; i < nb; ++i) {
+    bshape[i] = out->shape[i];
+    sc[i] = out->strides[i];
+    int ia = i - (nb - (a->ndim - 2)), ib = i - (nb - (b->ndim - 2));
+    sa[i] = (ia >= 0 && a->shape[ia] != 1) ? a->strides[ia] : 0;
+    sb[i] = (ib >= 0 && b->shape[ib] != 1) ? b->strides[ib] : 0;
+    if (ia >= 0) SK_REQUIRE(a->shape[ia] == 1 || a->shape[ia] == bshape[i], "matmul: batch dims do not broadcast");
+    if (ib >= 0) SK_REQUIRE(b->shape[ib] == 1 || b->shape[ib] == bshape[i], "matmul: batch dims do not broadcast");
+  }
+  const int64_t *strs[3] = {sa, sb, sc};
+  Collapsed<3> c;
+  collapse_dims<3>(nb, bshape, strs, c);
+  // innermost collapsed dim becomes the kernel's batch dim; outer ones loop on the host
+  const int last = c.ndim - 1;
+  g.batch = c.shape[last];
+  g.sa_b = c.strides[0][last]; g.sb_b = c.strides[1][last]; g.sc_b = c.strides[2][last];
+  int64_t outer = 1;
+  for (int i = 0; i < last; ++i) outer *= c.shape[i];
+  const int esz_a = dtype_size(a->dtype), esz_b = dtype_size(b->dtype);
+  for (int64_t o = 0; o < outer; ++o) {
+    int64_t rem = o, oa = 0, ob = 0, oc = 0;
+    for (int k = last - 1; k >= 0; --k) {
+      int64_t idx = rem % c.shape[k];
+      rem /= c.shape[k];
+      oa += idx * c.strides[0][k]; ob += idx * c.strides[1][k]; oc += idx * c.strides[2][k];
+    }
+    GemmProblem gi = g;
+    gi.a = (const char *)g.a + oa * esz_a;
+    gi.b = (const char *)g.b + ob * esz_b;
+    gi.c = g.c + oc;
+    if ((rc = run_one(gi, algo))) return rc;
+  }
+  return SK_OK;
+}
+
+}  // namespace sk
+
+using namespace sk;
+
+extern "C" {
+
+int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo) {
+  return matmul_impl(a, b, nullptr, out, SK_EPI_NONE, algo);
+}
+
+int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias, sk_array *out,
+                  int epilogue, int algo) {
+  SK_REQUIRE(epilogue >= SK_EPI_NONE && epilogue <= SK_EPI_RELU, "linear: bad epilogue %d", epilogue);
+  return matmul_impl(x, w, bias, out, epilogue, algo);
+}
+
+}  // extern "C"

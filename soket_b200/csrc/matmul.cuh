@@ -1,0 +1,37 @@
+// matmul.cuh -- shared GEMM problem description (SIMT + tcgen05 paths).
+#pragma once
+#include "common.cuh"
+
+namespace sk {
+
+// C[b] (M,N) = epilogue(A[b] (M,K) @ B[b] (K,N)); element strides.
+struct GemmProblem {
+  const void *a;
+  const void *b;
+  float *c;
+  const float *bias;
+  int a_dtype, b_dtype;
+  int64_t M, N, K;
+  int64_t sa_m, sa_k, sb_k, sb_n, ldc;
+  int64_t batch, sa_b, sb_b, sc_b;
+  int epilogue;
+};
+
+struct MMArgs {
+  const float *a, *b;
+  float *c;
+  const float *bias;
+  int64_t M, N, K;
+  int64_t sa_m, sa_k, sb_k, sb_n, ldc;
+  int64_t batch, sa_b, sb_b, sc_b;
+  int epilogue;
+};
+
+int launch_gemm_simt(const MMArgs &p);
+
+// tcgen05 path (matmul_tc.cu)
+bool tc_supported(const GemmProblem &g, int algo);
+bool tc_profitable(const GemmProblem &g);
+int launch_gemm_tc(const GemmProblem &g, int algo);
+
+}  // namespace sk

@@ -1,0 +1,133 @@
+// matmul_simt.cu -- CUDA-core fp32 GEMM (FFMA, exact fp32 products).
+//
+// The always-correct matmul: any M/N/K, any 2-D strides (so `.T` views from
+// soket/tensor/ops/backward.pyx:722,734 are consumed in place), one collapsed
+// batch dim.  It serves (a) shapes the tcgen05 path does not take (tiny /
+// misaligned, e.g. N = 10 classes), and (b) as the on-device cross-check of the
+// tensor-core kernels.  128x128x16 block tile, 8x8 register tile per thread,
+// double-buffered shared memory.
+#include "common.cuh"
+#include "matmul.cuh"
+
+namespace sk {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, NT = 256;
+
+// A_KFAST: A has unit (or small) stride along k -> load with k fastest across threads.
+// B_NFAST: B has unit stride along n.
+template <bool A_KFAST, bool B_NFAST>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(const MMArgs p) {
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t tiles_n = (p.N + BN - 1) / BN;
+  const int64_t tiles_m = (p.M + BM - 1) / BM;
+  const int64_t tiles = tiles_m * tiles_n;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 8x8 outputs
+
+  for (int64_t t = blockIdx.x; t < tiles * p.batch; t += gridDim.x) {
+    const int64_t bz = t / tiles;
+    const int64_t tt = t - bz * tiles;
+    const int64_t m0 = (tt / tiles_n) * BM, n0 = (tt % tiles_n) * BN;
+    const float *A = p.a + bz * p.sa_b;
+    const float *B = p.b + bz * p.sb_b;
+    float *C = p.c + bz * p.sc_b;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float ra[8], rb[8];
+    auto g_load = [&](int64_t k0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int idx = tid + e * NT;  // 0..2047 over the 128x16 tile
+        int m, k;
+        if (A_KFAST) { k = idx & 15; m = idx >> 4; } else { m = idx & 127; k = idx >> 7; }
+        int64_t gm = m0 + m, gk = k0 + k;
+        ra[e] = (gm < p.M && gk < p.K) ? A[gm * p.sa_m + gk * p.sa_k] : 0.f;
+        int n, kb;
+        if (B_NFAST) { n = idx & 127; kb = idx >> 7; } else { kb = idx & 15; n = idx >> 4; }
+        int64_t gn = n0 + n, gkb = k0 + kb;
+        rb[e] = (gn < p.N && gkb < p.K) ? B[gkb * p.sb_k + gn * p.sb_n] : 0.f;
+      }
+    };
+    auto s_store = [&](int buf) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        int idx = tid + e * NT;
+        int m, k;
+        if (A_KFAST) { k = idx & 15; m = idx >> 4; } else { m = idx & 127; k = idx >> 7; }
+        As[buf][k][m] = ra[e];
+        int n, kb;
+        if (B_NFAST) { n = idx & 127; kb = idx >> 7; } else { kb = idx & 15; n = idx >> 4; }
+        Bs[buf][kb][n] = rb[e];
+      }
+    };
+
+    g_load(0);
+    s_store(0);
+    __syncthreads();
+    int buf = 0;
+    for (int64_t k0 = 0; k0 < p.K; k0 += BK) {
+      const bool more = k0 + BK < p.K;
+      if (more) g_load(k0 + BK);
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float av[TM], bv[TN];
+        const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
+        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+        av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (more) {
+        s_store(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+      }
+    }
+    __syncthreads();  // smem is reused by the next tile of this block
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      int64_t gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (gm >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int64_t gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (gn >= p.N) continue;
+        float v = acc[i][j];
+        if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) v += p.bias[gn];
+        if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
+        C[gm * p.ldc + gn] = v;
+      }
+    }
+  }
+}
+
+int launch_gemm_simt(const MMArgs &p) {
+  if (p.M == 0 || p.N == 0 || p.batch == 0) return SK_OK;
+  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
+  const int64_t cap = (int64_t)ctx().num_sms * 2;
+  const int grid = (int)(tiles < cap ? tiles : cap);
+  const bool a_kfast = (p.sa_k == 1) || (p.sa_m != 1);
+  const bool b_nfast = (p.sb_n == 1) || (p.sb_k != 1);
+  if (a_kfast && b_nfast) gemm_simt_kernel<true, true><<<grid, NT, 0, stream()>>>(p);
+  else if (a_kfast) gemm_simt_kernel<true, false><<<grid, NT, 0, stream()>>>(p);
+  else if (b_nfast) gemm_simt_kernel<false, true><<<grid, NT, 0, stream()>>>(p);
+  else gemm_simt_kernel<false, false><<<grid, NT, 0, stream()>>>(p);
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+}  // namespace sk
