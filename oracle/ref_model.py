@@ -17,9 +17,20 @@ REF_DIR = os.path.join(HERE, "_ref")
 
 
 def import_reference():
-    """Import the built reference package; returns the `soket` module or None."""
+    """Import the built reference package; returns the `soket` module or None.
+
+    When soket_b200 is importable it is first registered under the module name the
+    reference imports for its GPU backend (soket_b200.compat.install), so the same
+    process can run the reference on its CPU device (NumPy -- the oracle) AND on
+    `soket.gpu()` (the sm_100a kernels -- the drop-in test)."""
     if not os.path.exists(os.path.join(REF_DIR, "soket", "__init__.py")):
         return None
+    if "soket" not in sys.modules:
+        try:
+            import soket_b200.compat as compat
+            compat.install()
+        except Exception:
+            pass
     if REF_DIR not in sys.path:
         sys.path.insert(0, REF_DIR)
     import warnings

@@ -410,7 +410,7 @@ cdef class ndarray:
 cdef ndarray _from_numpy(object arr, int code):
     """Upload a NumPy array (cast on the host to `code` first if needed)."""
     cdef object want = _NP_OF[code]
-    cdef object host = np.ascontiguousarray(arr, dtype=want)
+    cdef object host = np.asarray(arr, dtype=want, order='C')
     cdef ndarray out = _new_from_tuple(host.shape, code)
     cdef size_t nbytes = <size_t> host.nbytes
     cdef uintptr_t src

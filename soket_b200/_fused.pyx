@@ -1,0 +1,232 @@
+# cython: language_level=3, boundscheck=False, wraparound=False, cdivision=True
+"""soket_b200._fused -- Cython entry points of the fused nn / optimiser kernels.
+
+Each function replaces a sequence of backend array calls of the reference by one
+or two launches (include/soket_b200.h, "fused nn kernels" / "optimizers"):
+LayerNorm / BatchNorm forward+backward (forward.pyx:274-353, backward.pyx:1025-1132),
+softmax cross-entropy forward+backward (forward.pyx:250-271, backward.pyx:959-1022),
+Residual+ReLU (prototypes.pyx:272-273, model.py:34-37), Dropout
+(prototypes.pyx:746-760), bias gradient (autodiff.pyx:43-101), in-place gradient
+accumulation (autodiff.pyx:30-41), multi-tensor SGD / Adam (optim.pyx:82-269).
+All operands are contiguous float32 device arrays.
+"""
+from libc.stdint cimport int64_t
+from libc.stdlib cimport malloc, free
+
+from soket_b200._abi cimport *
+from soket_b200._core cimport ndarray, _new_array, _check, _fptr, _as_device
+
+
+cdef inline float *_opt(object a) except? NULL:
+    if a is None:
+        return NULL
+    return _fptr(<ndarray> a)
+
+
+cdef inline int _rows_cols(ndarray x, int64_t *rows, int64_t *cols) except -1:
+    if x._ndim < 2:
+        raise ValueError('expected an input of at least 2 dimensions')
+    cols[0] = x._shape[x._ndim - 1]
+    rows[0] = x._numel() // cols[0] if cols[0] else 0
+    return 0
+
+
+def layernorm_fwd(ndarray x, gamma=None, beta=None, residual=None, double eps=1e-5, bint relu=False):
+    """y = [relu]( [residual +] gamma * ((x - mean) * rstd) + beta ) over the last axis.
+    Returns (y, mean, rstd); mean/rstd have shape (rows,)."""
+    cdef int64_t rows, cols
+    _rows_cols(x, &rows, &cols)
+    cdef ndarray y = _new_array(x._ndim, x._shape, SK_F32)
+    cdef ndarray mean = _new_array(1, &rows, SK_F32)
+    cdef ndarray rstd = _new_array(1, &rows, SK_F32)
+    _check(sk_layernorm_fwd(_fptr(x), _opt(gamma), _opt(beta), _opt(residual), _fptr(y),
+                            _fptr(mean), _fptr(rstd), rows, cols, <float> eps, relu))
+    return y, mean, rstd
+
+
+def layernorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd,
+                  y_out=None, int mask_mode=0, bint want_dresidual=False, bint want_params=True):
+    """Returns (dx, dgamma, dbeta, dresidual)."""
+    cdef int64_t rows, cols
+    _rows_cols(x, &rows, &cols)
+    cdef ndarray dx = _new_array(x._ndim, x._shape, SK_F32)
+    cdef ndarray dg = None, db = None, dres = None
+    if want_params:
+        dg = _new_array(1, &cols, SK_F32)
+        db = _new_array(1, &cols, SK_F32)
+    if want_dresidual:
+        dres = _new_array(x._ndim, x._shape, SK_F32)
+    _check(sk_layernorm_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
+                            _opt(y_out), mask_mode, _fptr(dx), _opt(dg), _opt(db), _opt(dres),
+                            rows, cols))
+    return dx, dg, db, dres
+
+
+def batchnorm_fwd(ndarray x, gamma=None, beta=None, running_mean=None, running_var=None,
+                  double eps=1e-5, double momentum=0.1, bint relu=False):
+    """Training-mode BatchNorm1d over axis 0 of (rows, cols); running stats updated in
+    place when given.  Returns (y, mean, rstd) with mean/rstd of shape (cols,)."""
+    if x._ndim != 2:
+        raise ValueError('batchnorm_fwd: expected a 2-D input')
+    cdef int64_t rows = x._shape[0], cols = x._shape[1]
+    cdef ndarray y = _new_array(2, x._shape, SK_F32)
+    cdef ndarray mean = _new_array(1, &cols, SK_F32)
+    cdef ndarray rstd = _new_array(1, &cols, SK_F32)
+    _check(sk_batchnorm_fwd(_fptr(x), _opt(gamma), _opt(beta), _fptr(y), _fptr(mean), _fptr(rstd),
+                            _opt(running_mean), _opt(running_var), rows, cols, <float> eps,
+                            <float> momentum, relu))
+    return y, mean, rstd
+
+
+def batchnorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd,
+                  y_out=None, int mask_mode=0):
+    """Returns (dx, dgamma, dbeta)."""
+    if x._ndim != 2:
+        raise ValueError('batchnorm_bwd: expected a 2-D input')
+    cdef int64_t rows = x._shape[0], cols = x._shape[1]
+    cdef ndarray dx = _new_array(2, x._shape, SK_F32)
+    cdef ndarray dg = _new_array(1, &cols, SK_F32)
+    cdef ndarray db = _new_array(1, &cols, SK_F32)
+    _check(sk_batchnorm_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
+                            _opt(y_out), mask_mode, _fptr(dx), _fptr(dg), _fptr(db), rows, cols))
+    return dx, dg, db
+
+
+def softmax_ce(ndarray logits, ndarray labels, bint want_grad=True):
+    """Mean softmax cross-entropy of (rows, classes) logits against integer labels.
+    Returns (loss 0-d array, dlogits or None) in ONE pass (+ a tiny mean reduction)."""
+    if logits._ndim != 2 or labels._ndim != 1 or labels._shape[0] != logits._shape[0]:
+        raise ValueError('softmax_ce: expected (rows, classes) logits and (rows,) labels')
+    if not labels._is_contiguous():
+        labels = labels._compact()
+    cdef int64_t rows = logits._shape[0], classes = logits._shape[1]
+    cdef ndarray loss = _new_array(0, NULL, SK_F32)
+    cdef ndarray dl = None
+    if want_grad:
+        dl = _new_array(2, logits._shape, SK_F32)
+    _check(sk_softmax_ce_fwd_bwd(_fptr(logits), <const void *> labels._ptr, labels._code,
+                                 _fptr(loss), _opt(dl), NULL, rows, classes))
+    return loss, dl
+
+
+def add_relu(ndarray a, ndarray b):
+    """relu(a + b)."""
+    if a._numel() != b._numel():
+        raise ValueError('add_relu: size mismatch')
+    cdef ndarray out = _new_array(a._ndim, a._shape, SK_F32)
+    _check(sk_add_relu(_fptr(a), _fptr(b), _fptr(out), a._numel()))
+    return out
+
+
+def dropout(ndarray x, double keep, bint want_mask=True):
+    """(x * mask) * (1/keep), mask ~ Bernoulli(keep).  Returns (out, mask)."""
+    cdef ndarray out = _new_array(x._ndim, x._shape, SK_F32)
+    cdef ndarray mask = _new_array(x._ndim, x._shape, SK_F32) if want_mask else None
+    _check(sk_dropout_fwd(_fptr(x), _fptr(out), _opt(mask), x._numel(), <float> keep))
+    return out, mask
+
+
+def colsum(ndarray adj, y_out=None):
+    """Bias gradient: sum over axis 0 of (rows, cols); y_out applies a ReLU mask first."""
+    cdef int64_t rows, cols
+    _rows_cols(adj, &rows, &cols)
+    cdef ndarray out = _new_array(1, &cols, SK_F32)
+    _check(sk_colsum(_fptr(adj), _opt(y_out), _fptr(out), rows, cols))
+    return out
+
+
+def accumulate_(ndarray acc, ndarray part):
+    """acc += part, in place."""
+    if acc._numel() != part._numel():
+        raise ValueError('accumulate_: size mismatch')
+    _check(sk_accumulate(_fptr(acc), _fptr(part), acc._numel()))
+    return acc
+
+
+cdef class _PtrLists:
+    """Host-side pointer lists for the multi-tensor optimiser kernels."""
+    cdef float **p
+    cdef const float **g
+    cdef float **m
+    cdef float **v
+    cdef int64_t *sizes
+    cdef int n
+
+    def __cinit__(self, int n):
+        self.n = n
+        self.p = <float **> malloc(max(n, 1) * sizeof(float *))
+        self.g = <const float **> malloc(max(n, 1) * sizeof(float *))
+        self.m = <float **> malloc(max(n, 1) * sizeof(float *))
+        self.v = <float **> malloc(max(n, 1) * sizeof(float *))
+        self.sizes = <int64_t *> malloc(max(n, 1) * sizeof(int64_t))
+        if not (self.p and self.g and self.m and self.v and self.sizes):
+            raise MemoryError()
+
+    def __dealloc__(self):
+        free(self.p); free(<void *> self.g); free(self.m); free(self.v); free(self.sizes)
+
+
+def sgd_step(list params, list grads, double lr, double weight_decay=0.0, double grad_scale=1.0):
+    """In-place SGD over all tensors in ONE launch (optim.pyx:82-131)."""
+    cdef int n = len(params), i
+    cdef _PtrLists L = _PtrLists(n)
+    cdef ndarray p, g
+    for i in range(n):
+        p = <ndarray> params[i]; g = <ndarray> grads[i]
+        if p._numel() != g._numel():
+            raise ValueError(f'sgd_step: parameter {i} and its gradient differ in size')
+        L.p[i] = _fptr(p); L.g[i] = _fptr(g); L.sizes[i] = p._numel()
+    _check(sk_sgd_step(n, L.p, L.g, L.sizes, lr, weight_decay, grad_scale))
+
+
+def adam_step(list params, list grads, list m, list v, double lr, double beta1, double beta2,
+              double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+              bint first_step, double grad_scale=1.0):
+    """In-place Adam over all tensors in ONE launch (optim.pyx:201-269)."""
+    cdef int n = len(params), i
+    cdef _PtrLists L = _PtrLists(n)
+    cdef ndarray p, g
+    for i in range(n):
+        p = <ndarray> params[i]; g = <ndarray> grads[i]
+        if p._numel() != g._numel():
+            raise ValueError(f'adam_step: parameter {i} and its gradient differ in size')
+        L.p[i] = _fptr(p); L.g[i] = _fptr(g)
+        L.m[i] = _fptr(<ndarray> m[i]); L.v[i] = _fptr(<ndarray> v[i])
+        L.sizes[i] = p._numel()
+    _check(sk_adam_step(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
+                        one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale))
+
+
+# ---------------------------------------------------------------- data parallel
+def nccl_available():
+    return bool(sk_nccl_available())
+
+
+def nccl_unique_id():
+    cdef char buf[128]
+    _check(sk_nccl_unique_id(buf))
+    return bytes(buf[:128])
+
+
+def nccl_init(int rank, int world, bytes uid):
+    if len(uid) != 128:
+        raise ValueError('nccl_init: the unique id must be 128 bytes')
+    cdef const char *p = uid
+    _check(sk_nccl_init(rank, world, p))
+
+
+def nccl_allreduce(ndarray buf, bint on_comm_stream=False):
+    """In-place sum all-reduce of a contiguous fp32 buffer."""
+    _check(sk_nccl_allreduce(_fptr(buf), <size_t> buf._numel(), on_comm_stream))
+
+
+def nccl_broadcast(ndarray buf, int root=0):
+    _check(sk_nccl_broadcast(_fptr(buf), <size_t> buf._numel(), root))
+
+
+def nccl_wait():
+    _check(sk_nccl_wait())
+
+
+def nccl_destroy():
+    _check(sk_nccl_destroy())
