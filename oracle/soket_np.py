@@ -28,12 +28,35 @@ import numpy as np
 
 F32 = "float32"
 
+# Sensitivity probe (tests only): evaluate every matmul in float64 and round the
+# result to float32 -- an equally valid "fp32 implementation" whose distance to
+# the plain NumPy path measures how far rounding noise alone moves a trajectory.
+_HP_MATMUL = False
+
+
+class high_precision_matmul:
+    def __enter__(self):
+        global _HP_MATMUL
+        self._old = _HP_MATMUL
+        _HP_MATMUL = True
+
+    def __exit__(self, *exc):
+        global _HP_MATMUL
+        _HP_MATMUL = self._old
+        return False
+
+
+def _mm(a, b, **kw):
+    if _HP_MATMUL:
+        return np.matmul(a.astype(np.float64), b.astype(np.float64)).astype(F32)
+    return np.matmul(a, b, **kw)
+
 
 # ---------------------------------------------------------------- elementwise / linear
 def linear_fwd(X, W, b=None):
     """Linear._fast_forward, soket/nn/prototypes.pyx:108-115 -> _matmul_fwd
     (forward.pyx:172-178) then _elemwise_add_fwd (forward.pyx:7-13)."""
-    Y = np.matmul(X, W, dtype=F32)
+    Y = _mm(X, W, dtype=F32)
     if b is not None:
         Y = np.add(Y, b, dtype=F32)
     return Y
@@ -41,8 +64,8 @@ def linear_fwd(X, W, b=None):
 
 def matmul_bwd(adj, X, W, need_dx=True):
     """_matmul_bwd, soket/tensor/ops/backward.pyx:704-742: adj @ y.T, x.T @ adj."""
-    dX = np.matmul(adj, W.T) if need_dx else None
-    dW = np.matmul(X.T, adj)
+    dX = _mm(adj, W.T) if need_dx else None
+    dW = _mm(X.T, adj)
     return dX, dW
 
 
@@ -282,7 +305,7 @@ def kaiming_normal_std(shape, nonlinearity="relu"):
     """soket/nn/init.py:33-69 (quirk Q9): the value handed to randn as `std` is
     gain**2 / fan_in, i.e. the VARIANCE."""
     fan_in = shape[-2]
-    gain = math.sqrt(2.0)
+    gain = 1.4142  # soket/nn/init.py:47
     return gain * gain / fan_in
 
 

@@ -118,8 +118,8 @@ def build_cython(force=False, verbose=False):
     try:
         ext_modules = cythonize(
             exts, quiet=not verbose, include_path=[HERE],
-            compiler_directives=dict(language_level="3", boundscheck=False, wraparound=False,
-                                     initializedcheck=False, cdivision=True),
+            # boundscheck / wraparound are set per file in the `# cython:` headers
+            compiler_directives=dict(language_level="3", initializedcheck=False, cdivision=True),
             build_dir=os.path.join(HERE, "build", "cython"),
         )
         dist = Distribution({"name": "soket_b200", "ext_modules": ext_modules})

@@ -1,0 +1,17 @@
+# engine.pxd -- Tensor type shared with nn / optim.
+from soket_b200._core cimport ndarray
+
+
+cdef class Tensor:
+    cdef public ndarray _data
+    cdef public object _dtype
+    cdef public object _device
+    cdef public object _grad
+    cdef public bint _requires_grad
+    cdef public bint _retain_grad
+    cdef public object _op
+    cdef public tuple _inputs
+    cdef public list _partials
+    cdef public int _pending
+    cdef public int _visit
+    cdef public int _state

@@ -1,0 +1,123 @@
+# cython: language_level=3, boundscheck=True, wraparound=True, cdivision=True
+"""soket_b200.optim -- SGD and Adam (soket/optim.pyx) as single multi-tensor kernels.
+
+Same constructor arguments and the same arithmetic, quirks included (Q2: SGD's
+momentum branch only runs when momentum == 0, so every configuration is plain
+SGD; Q3: Adam's `maximize` negates the gradient after its last use), but one
+launch updates every parameter IN PLACE (the reference rebinds `p._data_` to a
+fresh array per parameter: optim.pyx:131,254) and Adam's moments stay resident.
+`grad_scale` folds the 1/W of data-parallel gradient averaging into the same
+kernel.
+"""
+from soket_b200.engine cimport Tensor
+from soket_b200 import _core as B
+from soket_b200 import _fused as F
+
+
+cdef class Optimizer:
+    """soket/optim.pyx:11-38."""
+    cdef public list _params
+    cdef public double grad_scale
+
+    def __init__(self, params):
+        self._params = list(params)
+        self.grad_scale = 1.0
+
+    def step(self):
+        raise NotImplementedError()
+
+    cdef tuple _live(self):
+        """Parameters that received a gradient (optim.pyx:100-102 skips the rest);
+        anything the multi-tensor kernel cannot take goes to the slow list."""
+        cdef list ps = [], gs = [], idx = []
+        cdef Tensor p, g
+        cdef int i = 0
+        for x in self._params:
+            p = <Tensor> x
+            if p._grad is not None:
+                g = <Tensor> p._grad
+                if not g._data.is_contiguous:
+                    g._data = B.ascontiguousarray(g._data)
+                if not p._data.is_contiguous:
+                    p._data = B.ascontiguousarray(p._data)
+                ps.append(p._data); gs.append(g._data); idx.append(i)
+            i += 1
+        return ps, gs, idx
+
+
+cdef class SGD(Optimizer):
+    """soket/optim.pyx:41-131."""
+    cdef public object _lr, _momentum, _weight_decay
+    cdef public bint _have_momentum, _have_weight_decay, _nesterov, _maximize
+
+    def __init__(self, params, lr=0.01, momentum=0.0, dampening=0.0, weight_decay=0.0,
+                 nesterov=False, maximize=False):
+        Optimizer.__init__(self, params)
+        self._lr = lr
+        self._momentum = momentum
+        self._have_momentum = (momentum == 0.0) is True     # quirk Q2, optim.pyx:72
+        self._weight_decay = weight_decay
+        self._have_weight_decay = (weight_decay != 0.0) is True
+        self._nesterov = nesterov is True
+        self._maximize = maximize is True
+        if dampening != 0.0 and self._have_momentum:
+            raise NotImplementedError('soket_b200.optim.SGD: dampening != 0 is not supported')
+
+    def step(self):
+        ps, gs, idx = self._live()
+        if not ps:
+            return
+        lr = -self._lr if self._maximize else self._lr      # optim.pyx:127-131: p - lr * (-g)
+        F.sgd_step(ps, gs, lr, self._weight_decay if self._have_weight_decay else 0.0, self.grad_scale)
+
+
+cdef class Adam(Optimizer):
+    """soket/optim.pyx:134-269."""
+    cdef public object _lr, _beta1, _beta2, _eps, _weight_decay
+    cdef public bint _have_weight_decay
+    cdef public object _t, _beta1_t, _beta2_t, _one_minus_beta1_t, _one_minus_beta2_t
+    cdef public list _u, _v
+
+    def __init__(self, params, lr=0.001, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, maximize=False):
+        Optimizer.__init__(self, params)
+        if len(betas) < 2:
+            raise ValueError('Invalid betas!')
+        for b in betas:
+            if type(b) is not float:
+                raise ValueError('Betas must be floats!')
+        self._lr = lr
+        self._beta1, self._beta2 = betas[0], betas[1]
+        self._eps = eps
+        self._weight_decay = weight_decay
+        self._have_weight_decay = (weight_decay != 0.0) is True
+        self._t = 1
+        self._beta1_t = self._beta1
+        self._beta2_t = self._beta2
+        self._one_minus_beta1_t = 1.0 - self._beta1_t
+        self._one_minus_beta2_t = 1.0 - self._beta2_t
+        self._u = [None] * len(self._params)
+        self._v = [None] * len(self._params)
+
+    def step(self):
+        ps, gs, idx = self._live()
+        # first-step parameters (no state yet) and the rest go to separate launches:
+        # optim.pyx:224-238 initialises m, v without the beta * 0 term
+        fresh = [k for k, i in enumerate(idx) if self._u[i] is None]
+        seen = [k for k, i in enumerate(idx) if self._u[i] is not None]
+        for k in fresh:
+            i = idx[k]
+            self._u[i] = B.empty(ps[k].shape, 'float32')
+            self._v[i] = B.empty(ps[k].shape, 'float32')
+        wd = self._weight_decay if self._have_weight_decay else 0.0
+        for group, first in ((fresh, True), (seen, False)):
+            if not group:
+                continue
+            F.adam_step([ps[k] for k in group], [gs[k] for k in group],
+                        [self._u[idx[k]] for k in group], [self._v[idx[k]] for k in group],
+                        self._lr, self._beta1, self._beta2, self._eps, wd,
+                        self._one_minus_beta1_t, self._one_minus_beta2_t, first, self.grad_scale)
+        self._t += 1
+        self._beta1_t *= self._beta1
+        self._beta2_t *= self._beta2
+        self._one_minus_beta1_t = 1.0 - self._beta1_t
+        self._one_minus_beta2_t = 1.0 - self._beta2_t

@@ -1,0 +1,78 @@
+"""CPU tests of host-side logic: dtype promotion table, scalar typing, DP sharding /
+rendezvous (world_size 2 over a TCPStore, gloo-free), bench helpers."""
+import multiprocessing as mp
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_promotion_table_matches_reference(ref_soket):
+    import soket_b200.engine as E
+    soket = ref_soket
+    names = E.DType._names
+    for a in names:
+        for b in names:
+            want = soket.promote_types(getattr(soket, a), getattr(soket, b)).name
+            got = E.promote_types(E._DTYPES[a], E._DTYPES[b]).name
+            assert got == want, (a, b, got, want)
+
+
+def test_scalar_dtypes_and_dtype_api():
+    import soket_b200.engine as E
+    assert E._scalar_dtype(1) is E.int32 and E._scalar_dtype(1.0) is E.float32 and E._scalar_dtype(True) is E.bool_
+    with pytest.raises(ValueError):
+        E.DType("complex64")
+    assert E.DType("float32") == E.float32 and str(E.float32) == "float32"
+    assert E.promote_types(E.bool_, E.uint8) is E.uint8
+    assert E.promote_types(E.int64, E.uint64).name == "float32"   # reference table, not NumPy's float64
+
+
+def test_shard_rows_partitions_the_batch():
+    from soket_b200.dp import shard_rows
+    for n, w in ((8192, 1), (8192, 2), (8192, 8), (100, 4)):
+        seen = np.zeros(n, int)
+        for r in range(w):
+            seen[shard_rows(n, r, w)] += 1
+        assert np.all(seen == 1)
+    with pytest.raises(ValueError):
+        shard_rows(100, 0, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from soket_b200 import dp
+    env = dp.read_env()
+    rdv = dp.Rendezvous(env, timeout_s=60)
+    uid = dp.exchange_unique_id(rdv, lambda: bytes(range(128)))
+    rdv.barrier()
+    vals = rdv.all_gather_float(1.5 + rank)
+    rdv.barrier()
+    q.put((rank, uid, vals, dp.shard_rows(64, env.rank, env.world)))
+
+
+def test_rendezvous_world_size_2():
+    """The N>1 host path (unique-id hand-off, barrier, scalar gather) on CPU."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1] == out[1][1] == bytes(range(128))
+    assert out[0][2] == out[1][2] == [1.5, 2.5]
+    assert out[0][3] == slice(0, 32) and out[1][3] == slice(32, 64)
