@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- MLPResNet training throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU, NCCL
+
+Workload (BASELINE.json configs[3]/[4]): the wide MLPResNet of
+examples/mlp_resnet/model.py -- 784 -> 4096, 8 residual blocks (Linear, LayerNorm,
+ReLU, Dropout(0.01), Linear, LayerNorm; residual add; ReLU), -> 10 classes -- in the
+`self.fn`-retaining variant that makes all 68 tensors (271.9 M parameters) trainable
+(quirk Q1), batch 8192 PER GPU, Adam(lr=1e-3), fp32, synthetic MNIST-shaped data,
+random-init weights (kaiming_normal, quirk Q9).  One step = forward + softmax-CE +
+backward + Adam update.  Data-parallel runs (N > 1) keep 8192 rows per GPU (weak
+scaling) and all-reduce every gradient over NCCL, overlapped with backward.
+
+One JSON line on stdout (rank 0):
+  value      samples/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        samples/s through the public API with per-step pinned-host -> device
+             copies of the batch and a device -> host read of the loss
+  roofline   the dominant kernel family (the GEMMs): achieved algorithmic TFLOP/s,
+             measured live with CUDA events around every GEMM launch of the timed
+             region, against the measured bf16 tensor peak of MEASURED_PEAKS.json
+  cpu_baseline  the reference (oracle/_ref, else the NumPy port) on the host cores,
+             on a bounded sample of the same workload (rank 0, N = 1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, HIDDEN, BLOCKS, CLASSES = 784, 4096, 8, 10
+BATCH_PER_GPU = 8192
+DROP_P = 0.01
+LR = 1e-3
+
+
+def flops_per_step(batch, hidden=HIDDEN, blocks=BLOCKS, dim=DIM, classes=CLASSES):
+    """2*M*N*K over every GEMM of forward + backward (no dX for the first layer)."""
+    fwd = 2.0 * batch * (dim * hidden + blocks * 2 * hidden * hidden + hidden * classes)
+    bwd = 2.0 * batch * (dim * hidden + blocks * 2 * 2 * hidden * hidden + 2 * hidden * classes)
+    return fwd + bwd
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # under load = the upper half of the samples (idle samples bracket the region)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- model builders
+def build_model(nn, hidden, blocks, drop_p=DROP_P):
+    """examples/mlp_resnet/model.py:17-58 out of the given `nn` namespace (the
+    reference's soket.nn or soket_b200.nn), keeping `self.fn` so the inner layers are
+    visible to parameters() / modules() / train() (quirk Q1)."""
+    class ResidualBlock(nn.Sequential):
+        def __init__(self, dim, hid):
+            fn = nn.Sequential(nn.Linear(dim, hid), nn.LayerNorm(hid), nn.ReLU(), nn.Dropout(p=drop_p),
+                               nn.Linear(hid, hid), nn.LayerNorm(hid))
+            super().__init__(nn.Residual(fn), nn.ReLU())
+            self.fn = fn
+
+    class MLPResNet(nn.Sequential):
+        def __init__(self):
+            super().__init__(nn.Linear(DIM, hidden), nn.ReLU(),
+                             *[ResidualBlock(hidden, hidden) for _ in range(blocks)],
+                             nn.Linear(hidden, CLASSES))
+
+    return MLPResNet()
+
+
+def synthetic_batch(batch, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random((batch, DIM), dtype=np.float32)
+    y = rng.integers(0, CLASSES, batch).astype(np.uint8)
+    return X, y
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_time(batch, steps, warmup, hidden=HIDDEN, blocks=BLOCKS):
+    """Time the reference's own CPU implementation (oracle/_ref) -- or, if it is not
+    built, the NumPy port -- on `batch` rows of the same model.  Returns
+    (seconds_per_step, kind, cores)."""
+    from oracle import ref_model
+    cores = os.cpu_count() or 1
+    soket = ref_model.import_reference()
+    X, y = synthetic_batch(batch, 0)
+    if soket is not None:
+        import soket.nn as rnn
+        from soket.nn.init import kaiming_normal
+        from soket.optim import Adam
+        np.random.seed(0)
+        model = build_model(rnn, hidden, blocks)
+        for m in model.modules():
+            if type(m).__name__ == "Linear":
+                kaiming_normal(m.weight)
+        opt = Adam(model.parameters(), lr=LR)
+        crit = rnn.SoftmaxCrossEntropyLoss()
+        model.train(True)
+        Xt, yt = soket.Tensor(X), soket.Tensor(y)
+
+        def step():
+            loss = crit(model(Xt), yt)
+            loss.backward()
+            opt.step()
+            return loss.item()
+        kind = "reference"
+    else:
+        from oracle import soket_np as O
+        om = O.MLPResNet(DIM, hidden, blocks, CLASSES, norm="layer")
+        om.init_kaiming(0)
+        opt = O.Adam(len(om.names()), lr=LR)
+
+        def step():
+            return om.train_step(X, y, opt)[0]
+        kind = "port"
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / max(steps, 1), kind, cores
+
+
+def run_reference(args, env):
+    if env.rank != 0:
+        return
+    sample = args.cpu_sample_batch
+    sec, kind, cores = cpu_reference_step_time(sample, args.steps, min(args.warmup, 1))
+    value = sample / sec
+    line = {
+        "impl": "reference", "metric": "mlpresnet_train_samples_per_s", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} Adam step(s) of the same model on {sample} rows per step "
+                                   f"(full batch is {BATCH_PER_GPU}); NumPy/OpenBLAS threads = all host cores"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, LayerNorm, "
+                    f"dropout={DROP_P}) train step, Adam lr=1e-3, fp32, all {4 + 8 * args.blocks} tensors trainable "
+                    f"(BASELINE.json configs[3]; configs[4] for N>1)",
+        "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+        "parallelism": f"dp{world}" if world > 1 else "single",
+        "l2": "per-step working set (activations + 1.09 GB of weights) >> 126 MB L2; no explicit flush",
+    }
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, env):
+    import soket_b200 as sk
+    from soket_b200 import dp, nn
+    from soket_b200 import engine as E
+    from soket_b200.optim import Adam
+    import soket_b200.api as soket
+
+    sk.init(env.local_rank)
+    rdv = dp.Rendezvous(env) if env.world > 1 else None
+
+    sk.random.seed(1234)          # identical initial weights on every rank
+    model = build_model(nn, args.hidden, args.blocks)
+    for m in model.modules():
+        if type(m).__name__ == "Linear":
+            nn.kaiming_normal(m.weight)
+    params = list(model.parameters())
+    n_params = sum(int(p.size) for p in params)
+    opt = Adam(params, lr=LR)
+    ddp = dp.DataParallel(opt, rdv)
+    ddp.broadcast_parameters(0)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    model.train(True)
+    sk.random.seed(99 + env.rank)  # dropout masks differ per rank
+
+    batch = args.batch
+    Xh, yh = synthetic_batch(batch, 100 + env.rank)
+    Xd, yd = soket.Tensor(Xh), soket.Tensor(yh)
+    pin_x = sk.PinnedBuffer(Xh.shape, "float32"); pin_x.array[...] = Xh
+    pin_y = sk.PinnedBuffer(yh.shape, "uint8"); pin_y.array[...] = yh
+    pin_loss = sk.PinnedBuffer((1,), "float32")
+    stage_x = sk.empty(Xh.shape, "float32")
+    stage_y = sk.empty(yh.shape, "uint8")
+
+    def step_resident():
+        loss = crit(model(Xd), yd)
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        pin_x.copy_to_device(stage_x)
+        pin_y.copy_to_device(stage_y)
+        loss = crit(model(E.Tensor._const(stage_x)), E.Tensor._const(stage_y))
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        pin_loss.copy_from_device(loss._data.reshape(1))
+        sk.synchronize()
+        return float(pin_loss.array[0])
+
+    def barrier():
+        sk.synchronize()
+        if rdv is not None:
+            rdv.barrier()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------
+    clocks = ClockSampler(env.local_rank)
+    if env.rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    sk.profile_reset()
+    sk.profile_enable(True)
+    launches0 = sk.launch_count()
+    barrier()
+    ev0, ev1 = sk.Event(), sk.Event()
+    ev0.record()
+    last = None
+    for _ in range(args.steps):
+        last = step_resident()
+    ev1.record()
+    ev1.synchronize()
+    barrier()
+    ms = ev0.elapsed_ms(ev1)
+    launches = sk.launch_count() - launches0
+    prof = sk.profile_collect()
+    sk.profile_enable(False)
+    loss_value = last.item()
+
+    # ---- timed region 2: end to end (pinned host -> device every step, loss -> host) -------
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = sk.Event(), sk.Event()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    e1.synchronize()
+    barrier()
+    ms_e2e = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    clock_info = clocks.stop() if env.rank == 0 else None
+
+    if rdv is not None:
+        ms = max(rdv.all_gather_float(ms))
+        ms_e2e = max(rdv.all_gather_float(ms_e2e))
+    ms_per_step = ms / args.steps
+    value = batch * env.world / (ms_per_step * 1e-3)
+    e2e_value = batch * env.world / (ms_e2e / args.steps * 1e-3)
+
+    if env.rank == 0:
+        peaks, peak_kind = load_peaks()
+        gemm = prof.get("gemm_tc") or prof.get("gemm_simt") or {"launches": 0, "ms": 0.0, "work": 0.0}
+        fam = "gemm_tc" if "gemm_tc" in prof else "gemm_simt"
+        achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
+        peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+        families = {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
+                        "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k.startswith("gemm") else 1e9)) if v["ms"] else 0.0,
+                        "unit": "TFLOP/s" if k.startswith("gemm") else "GB/s"}
+                    for k, v in prof.items()}
+        line = {
+            "metric": "mlpresnet_train_samples_per_s", "value": value, "unit": "samples/s",
+            "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, env.world),
+            "e2e": {"value": e2e_value, "unit": "samples/s",
+                    "h2d_bytes_per_step": int(Xh.nbytes + yh.nbytes), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clock_info,
+            "roofline": {
+                "bound": "tensor", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind}); the path computes fp32 "
+                               f"GEMMs (3xTF32 on tcgen05 when gemm_tc, FFMA when gemm_simt), numerator = 2*M*N*K",
+                "gemm_launches": gemm["launches"], "gemm_ms_per_step": gemm["ms"] / args.steps,
+                "share_of_step": gemm["ms"] / ms if ms else None,
+            },
+            "kernel_families": families,
+            "model_flops_per_step": flops_per_step(batch, args.hidden, args.blocks),
+            "params": n_params, "final_loss": loss_value,
+        }
+        if env.world == 1 and not args.no_cpu_baseline:
+            sec, kind, cores = cpu_reference_step_time(args.cpu_sample_batch, 1, 1, args.hidden, args.blocks)
+            line["cpu_baseline"] = {
+                "value": args.cpu_sample_batch / sec, "unit": "samples/s", "cores": cores, "kind": kind,
+                "sample": f"1 Adam step of the same model on {args.cpu_sample_batch} rows after 1 warm-up step "
+                          f"(full batch is {batch}); NumPy/OpenBLAS threads = all host cores"}
+        print(json.dumps(line), flush=True)
+    ddp.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="rows per GPU")
+    ap.add_argument("--hidden", type=int, default=HIDDEN)
+    ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--cpu-sample-batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    from soket_b200 import dp
+    env = dp.read_env()
+    if args.impl == "reference":
+        run_reference(args, env)
+    else:
+        run_ours(args, env)
+
+
+if __name__ == "__main__":
+    main()

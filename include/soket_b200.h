@@ -93,6 +93,28 @@ int sk_event_destroy(void *ev);
 uint64_t sk_launch_count(void); /* kernels this library launched so far */
 int sk_flush_l2(void);          /* overwrite a >L2 scratch buffer */
 
+/* Per-kernel-family timing for the roofline numbers: when enabled, every launch of
+ * an instrumented family is bracketed by CUDA events on the compute stream;
+ * sk_prof_collect() synchronises and returns, for one family, the launch count,
+ * the summed device time and the summed ALGORITHMIC work (flops for GEMMs, bytes
+ * for memory-bound kernels) since the last sk_prof_reset(). */
+typedef enum {
+  SK_PROF_GEMM_TC = 0,
+  SK_PROF_GEMM_SIMT = 1,
+  SK_PROF_LN_FWD = 2,
+  SK_PROF_LN_BWD = 3,
+  SK_PROF_EWISE = 4,
+  SK_PROF_REDUCE = 5,
+  SK_PROF_OPTIM = 6,
+  SK_PROF_COPY = 7,
+  SK_PROF_BN = 8,
+  SK_PROF_LOSS = 9,
+  SK_PROF_NUM = 10
+} sk_prof_family;
+int sk_prof_enable(int on);
+int sk_prof_reset(void);
+int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *total_work);
+
 /* CUDA-graph capture of a static-shape step */
 int sk_graph_begin(void);
 int sk_graph_end(void **graph_exec);

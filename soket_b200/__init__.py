@@ -19,7 +19,7 @@ import os as _os
 _here = _os.path.dirname(_os.path.abspath(__file__))
 if not _os.path.exists(_os.path.join(_here, "lib", "libsoketb200.so")):
     raise ImportError(
-        "soket_b200: lib/libsoketb200.so is not built -- run `python -m soket_b200.build` "
+        "soket_b200: lib/libsoketb200.so is not built -- run `python soket_b200/build.py` "
         "(nvcc, sm_100a).  There is no CPU fallback.")
 
 try:
@@ -27,7 +27,7 @@ try:
 except ImportError as _e:  # pragma: no cover - build problem, fail loudly
     raise ImportError(
         f"soket_b200: the Cython extension soket_b200._core failed to import ({_e}); "
-        "run `python -m soket_b200.build`.  There is no CPU fallback.") from _e
+        "run `python soket_b200/build.py`.  There is no CPU fallback.") from _e
 
 from ._core import (  # noqa: F401,E402
     ndarray, array, asarray, asnumpy, copy, to_bf16, bfloat16,
@@ -41,6 +41,7 @@ from ._core import (  # noqa: F401,E402
     MM_AUTO, MM_SIMT, MM_TF32X3, MM_TF32, MM_BF16,
     random, device_count, is_available, init, synchronize, launch_count, flush_l2,
     memory_stats, empty_cache, version, Event, Graph, PinnedBuffer,
+    profile_enable, profile_reset, profile_collect,
 )
 
 __version__ = "0.1.0"

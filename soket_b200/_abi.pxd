@@ -93,6 +93,10 @@ cdef extern from "soket_b200.h" nogil:
     uint64_t sk_launch_count()
     int sk_flush_l2()
 
+    int sk_prof_enable(int on)
+    int sk_prof_reset()
+    int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *total_work)
+
     int sk_graph_begin()
     int sk_graph_end(void **graph_exec)
     int sk_graph_launch(void *graph_exec)

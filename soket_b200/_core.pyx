@@ -1391,6 +1391,30 @@ def flush_l2():
     _check(sk_flush_l2())
 
 
+PROF_FAMILIES = ('gemm_tc', 'gemm_simt', 'ln_fwd', 'ln_bwd', 'ewise', 'reduce', 'optim', 'copy', 'bn', 'loss')
+
+
+def profile_enable(bint on=True):
+    """Bracket every instrumented kernel family with CUDA events (roofline numbers)."""
+    _check(sk_prof_enable(on))
+
+
+def profile_reset():
+    _check(sk_prof_reset())
+
+
+def profile_collect():
+    """{family: {'launches', 'ms', 'work'}}; work = flops (gemm_*) or algorithmic bytes."""
+    cdef int64_t n = 0
+    cdef double ms = 0, work = 0
+    out = {}
+    for i, name in enumerate(PROF_FAMILIES):
+        _check(sk_prof_collect(i, &n, &ms, &work))
+        if n:
+            out[name] = {'launches': int(n), 'ms': ms, 'work': work}
+    return out
+
+
 def memory_stats():
     cdef size_t a = 0, b = 0, c = 0
     sk_mem_stats(&a, &b, &c)

@@ -1,6 +1,6 @@
 """Build script: libsoketb200.so (nvcc, sm_100a) + the Cython host extension.
 
-    python -m soket_b200.build [--force] [--verbose]
+    python soket_b200/build.py [--force] [--verbose]
 
 Everything is built IN-TREE (``soket_b200/lib/libsoketb200.so`` and
 ``soket_b200/_core.*.so``) so the artefacts travel with the repository

@@ -51,6 +51,23 @@ int ensure_init();
 void note_launch();
 inline cudaStream_t stream() { return ctx().stream; }
 
+// ---- per-family profiling (sk_prof_*) -------------------------------------------
+// Usage inside a launcher:  ProfScope ps(SK_PROF_GEMM_TC, flops);  ... launch ...
+bool prof_on();
+void prof_begin(int family);
+void prof_end(int family, double work);
+struct ProfScope {
+  int family;
+  double work;
+  bool on;
+  ProfScope(int f, double w) : family(f), work(w), on(prof_on()) {
+    if (on) prof_begin(family);
+  }
+  ~ProfScope() {
+    if (on) prof_end(family, work);
+  }
+};
+
 // ---- dtype helpers ----------------------------------------------------------
 __host__ __device__ inline int dtype_size(int dt) {
   switch (dt) {

@@ -601,6 +601,7 @@ int sk_ewise_binary(int op, const sk_array *a, const sk_array *b, sk_array *out)
   if (all_f32 && aligned16(a->data) && aligned16(b->data) && aligned16(out->data)) {
     if (c.ndim == 1 && c.strides[0][0] == 1 && c.strides[1][0] == 1 && c.strides[2][0] == 1) {
       int grid = grid_for((n + 3) / 4, kThreads * kUnroll, 8);
+      ProfScope ps(SK_PROF_EWISE, (double)n * 12.0);
 #define CALL(OP) binary_f32_vec<OP><<<grid, kThreads, 0, stream()>>>((const float *)a->data, (const float *)b->data, (float *)out->data, n)
       SK_BIN_SWITCH(op, CALL)
 #undef CALL
@@ -622,6 +623,7 @@ int sk_ewise_binary(int op, const sk_array *a, const sk_array *b, sk_array *out)
       };
       if (out_ok && (C % 4 == 0) && opnd_ok(0) && opnd_ok(1)) {
         int grid = grid_for(R * (C / 4), kThreads, 8);
+        ProfScope ps(SK_PROF_EWISE, (double)n * 4.0 + ((s0(0) && s1(0)) ? (double)n * 4.0 : 0.0) + ((s0(1) && s1(1)) ? (double)n * 4.0 : 0.0));
 #define CALL(OP) binary_f32_bcast2d<OP><<<grid, kThreads, 0, stream()>>>((const float *)a->data, s0(0), (int)s1(0), (const float *)b->data, s0(1), (int)s1(1), (float *)out->data, R, C / 4)
         SK_BIN_SWITCH(op, CALL)
 #undef CALL
@@ -663,6 +665,7 @@ int sk_ewise_scalar(int op, const sk_array *a, double fscalar, int64_t iscalar, 
   if (a->dtype == SK_F32 && out->dtype == SK_F32 && !is_cmp && c.ndim == 1 &&
       c.strides[0][0] == 1 && c.strides[1][0] == 1 && aligned16(a->data) && aligned16(out->data)) {
     int grid = grid_for((n + 3) / 4, kThreads * kUnroll, 8);
+    ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
     float s = (float)fscalar;
     int pk = pow_kind(fscalar);
     if (op == SK_OP_MAXIMUM && s == 0.f) {
@@ -709,6 +712,7 @@ int sk_ewise_unary(int op, const sk_array *a, sk_array *out) {
   if (a->dtype == SK_F32 && out->dtype == SK_F32 && c.ndim == 1 && c.strides[0][0] == 1 &&
       c.strides[1][0] == 1 && aligned16(a->data) && aligned16(out->data)) {
     int grid = grid_for((n + 3) / 4, kThreads * kUnroll, 8);
+    ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
     const float *ap = (const float *)a->data;
     float *op_ = (float *)out->data;
     switch (op) {
@@ -756,6 +760,7 @@ int sk_copy(const sk_array *src, sk_array *dst) {
       int64_t R = c.shape[0], C = c.shape[1];
       int64_t tiles = ((R + 31) / 32) * ((C + 31) / 32);
       int grid = (int)(tiles < (int64_t)ctx().num_sms * 16 ? tiles : (int64_t)ctx().num_sms * 16);
+      ProfScope ps(SK_PROF_COPY, (double)n * esz * 2.0);
       if (esz == 4) transpose_tiled<uint32_t><<<grid, 256, 0, stream()>>>((const uint32_t *)src->data, (uint32_t *)dst->data, R, C, c.strides[0][1], c.strides[1][0]);
       else if (esz == 8) transpose_tiled<uint64_t><<<grid, 256, 0, stream()>>>((const uint64_t *)src->data, (uint64_t *)dst->data, R, C, c.strides[0][1], c.strides[1][0]);
       else if (esz == 2) transpose_tiled<uint16_t><<<grid, 256, 0, stream()>>>((const uint16_t *)src->data, (uint16_t *)dst->data, R, C, c.strides[0][1], c.strides[1][0]);
@@ -770,6 +775,7 @@ int sk_copy(const sk_array *src, sk_array *dst) {
     d.mode = 4;
     fill_desc<2>(d, c, 0, -1, 1);
     int grid = grid_for(d.n, kThreads, 16);
+    ProfScope ps(SK_PROF_COPY, (double)d.n * esz * 2.0);
     if (esz == 4) generic_copy_raw<uint32_t><<<grid, kThreads, 0, stream()>>>(d);
     else if (esz == 8) generic_copy_raw<uint64_t><<<grid, kThreads, 0, stream()>>>(d);
     else if (esz == 2) generic_copy_raw<uint16_t><<<grid, kThreads, 0, stream()>>>(d);
@@ -850,6 +856,7 @@ int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out) {
   const int64_t n = numel(out);
   if (n == 0) return SK_OK;
   int grid = grid_for((n + 3) / 4, kThreads * kUnroll, 8);
+  ProfScope ps(SK_PROF_EWISE, (double)n * 12.0);
   relu_bwd_f32_vec<<<grid, kThreads, 0, stream()>>>((const float *)x->data, (const float *)adj->data, (float *)out->data, n);
   SK_LAUNCH_CHECK();
   return SK_OK;

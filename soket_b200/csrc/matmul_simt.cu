@@ -120,6 +120,7 @@ int launch_gemm_simt(const MMArgs &p) {
   const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
   const int64_t cap = (int64_t)ctx().num_sms * 2;
   const int grid = (int)(tiles < cap ? tiles : cap);
+  ProfScope ps(SK_PROF_GEMM_SIMT, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
   const bool a_kfast = (p.sa_k == 1) || (p.sa_m != 1);
   const bool b_nfast = (p.sb_n == 1) || (p.sb_k != 1);
   if (a_kfast && b_nfast) gemm_simt_kernel<true, true><<<grid, NT, 0, stream()>>>(p);

@@ -1,11 +1,550 @@
-// matmul_tc.cu -- tcgen05 / TMEM / TMA GEMM (placeholder until the kernel lands).
+// matmul_tc.cu -- tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+// C (M,N) fp32 = epilogue(A (M,K) @ B (K,N)), operands fp32 (kind::tf32, optionally the
+// error-compensated 3xTF32 scheme) or bf16 (kind::f16), each either K-major or
+// MN-major in global memory -- i.e. row-major matrices AND their `.T` views are
+// consumed in place (soket/tensor/ops/forward.pyx:172-178, backward.pyx:720-736).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (128B swizzle) into a STAGES-deep
+//               shared-memory ring, completion on `full` mbarriers
+//   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma
+//               (cta_group::1, M=128, N=BN, K=32 bytes per instruction) reading A/B
+//               through shared-memory matrix descriptors, fp32 accumulators in TMEM
+//               (2 x BN columns, double buffered); tcgen05.commit releases ring slots
+//               and publishes finished accumulators
+//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 -> registers -> (+bias)(ReLU) -> global
+//
+// 3xTF32 (fp32 parity at 1e-5): kind::tf32 truncates operands to 10 mantissa bits
+// (~1e-3).  With hi = tf32(x) taken by the hardware from the raw fp32 bits and
+// lo = x - hi (exact, prepared by a small elementwise pass), A@B ~= Ahi@Bhi + Ahi@Blo +
+// Alo@Bhi accumulated in fp32 in TMEM restores ~2^-21 relative accuracy at 1/3 of the
+// TF32 rate.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "matmul.cuh"
+
 namespace sk {
-bool tc_supported(const GemmProblem &, int) { return false; }
-bool tc_profitable(const GemmProblem &) { return false; }
-int launch_gemm_tc(const GemmProblem &, int) {
-  set_error("tcgen05 GEMM not built");
-  return SK_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------ device PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (CUDA error at the next sync) instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05 "smem descriptor", SWIZZLE_128B):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte
+//   offset >> 4   [46,48) version = 1 (Blackwell)   [61,64) layout type (2 = 128B swizzle)
+//   layout type 1 = "128B swizzle with 32-byte atoms": the ONLY layout tcgen05 accepts
+//   for MN-major 32-bit (tf32) operands -- 4 K-rows of 128 B per atom, the four 32 B
+//   chunks of a row XOR-ed with (row % 4); TMA writes it with SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// Instruction descriptor (upper 32 bits of the "runtime idesc"):
+//   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 f16, 1 bf16, 2 tf32)
+//   [15] A major (0 K, 1 MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ kernel
+enum { KIND_TF32 = 0, KIND_TF32X3 = 1, KIND_BF16 = 2 };
+
+struct TcParams {
+  float *c;
+  const float *bias;
+  int64_t ldc;
+  int M, N, K;
+  int epilogue;
+  int tiles_m, tiles_n;
+};
+
+constexpr int BM = 128;
+constexpr int kTcThreads = 192;
+
+template <int KIND, int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo,
+               const TcParams p) {
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr bool X3 = KIND == KIND_TF32X3;
+  constexpr int ES = BF16 ? 2 : 4;            // operand element size
+  constexpr int BK = 128 / ES;                // elements per 128-byte swizzle row = K per stage
+  constexpr int UK = 32 / ES;                 // K per tcgen05.mma
+  constexpr int SLAB = 128 / ES;              // MN elements per 128-byte row (MN-major operands)
+  constexpr uint32_t A_BYTES = BM * 128;      // BM x BK elements
+  constexpr uint32_t B_BYTES = BN * 128;
+  constexpr uint32_t STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr uint32_t A_LO_OFF = A_BYTES;
+  constexpr uint32_t B_OFF = (X3 ? 2 : 1) * A_BYTES;
+  constexpr uint32_t B_LO_OFF = B_OFF + B_BYTES;
+  // descriptor strides.  K-major: 8-row groups 1024 B apart.  MN-major: 128-byte rows run
+  // along MN, 8 K-rows per swizzle atom (1024 B), MN slabs BK*128 B apart.
+  // fp32 MN-major: 4-row (512 B) atoms of the 32B-atom swizzle, descriptor layout type 1.
+  constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, A_SBO = (A_MN && !BF16) ? 512 : 1024;
+  constexpr uint32_t B_LBO = B_MN ? BK * 128 : 0, B_SBO = (B_MN && !BF16) ? 512 : 1024;
+  constexpr uint32_t A_LT = (A_MN && !BF16) ? 1 : 2, B_LT = (B_MN && !BF16) ? 1 : 2;
+  constexpr uint32_t A_KSTEP = A_MN ? UK * 128 : 32;   // bytes to advance per UK along K
+  constexpr uint32_t B_KSTEP = B_MN ? UK * 128 : 32;
+  constexpr uint32_t IDESC = make_idesc(BF16 ? 1 : 2, A_MN, B_MN, BM, BN);
+  constexpr int TMEM_COLS = 2 * BN;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle (address bits [7,10) select the XOR)
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t *full_bar = bars;                    // [STAGES]
+  uint64_t *empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t *tfull_bar = bars + 2 * STAGES;      // [2]
+  uint64_t *tempty_bar = bars + 2 * STAGES + 2; // [2]
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (X3) { tma_prefetch_desc(&map_alo); tma_prefetch_desc(&map_blo); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / SLAB; ++j) {
+              tma_load_2d(sbase + j * (BK * 128), &map_a, fb, m0 + j * SLAB, k0);
+              if (X3) tma_load_2d(sbase + A_LO_OFF + j * (BK * 128), &map_alo, fb, m0 + j * SLAB, k0);
+            }
+          } else {
+            tma_load_2d(sbase, &map_a, fb, k0, m0);
+            if (X3) tma_load_2d(sbase + A_LO_OFF, &map_alo, fb, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / SLAB; ++j) {
+              tma_load_2d(sbase + B_OFF + j * (BK * 128), &map_b, fb, n0 + j * SLAB, k0);
+              if (X3) tma_load_2d(sbase + B_LO_OFF + j * (BK * 128), &map_blo, fb, n0 + j * SLAB, k0);
+            }
+          } else {
+            tma_load_2d(sbase + B_OFF, &map_b, fb, k0, n0);
+            if (X3) tma_load_2d(sbase + B_LO_OFF, &map_blo, fb, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);   // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = make_smem_desc(sbase + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+            const uint64_t db = make_smem_desc(sbase + B_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+            tc_mma<BF16>(d_tmem, da, db, IDESC, (kb | k) != 0);
+            if (X3) {
+              const uint64_t dalo = make_smem_desc(sbase + A_LO_OFF + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t dblo = make_smem_desc(sbase + B_LO_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+              tc_mma<BF16>(d_tmem, da, dblo, IDESC, 1);     // Ahi @ Blo
+              tc_mma<BF16>(d_tmem, dalo, db, IDESC, 1);     // Alo @ Bhi
+            }
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));              // slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));                  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.c) & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float *crow = p.c + (int64_t)row * p.ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;           // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if (row < p.M) {
+          const int col = n0 + c0;
+          const bool full = col + 32 <= p.N;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {
+              if (full || col + j < p.N) v += __ldg(p.bias + col + j);
+            }
+            if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
+            r[j] = __float_as_uint(v);
+          }
+          if (full && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4 *>(crow + col + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) crow[col + j] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// lo = tf32_rn(x - tf32_trunc(x)) for a (rows, cols) matrix with unit column stride.
+// The hardware takes hi = tf32_trunc(x) from the raw fp32 bits, so x - hi is exact; the
+// tensor core would TRUNCATE lo to 10 mantissa bits too, and a truncation always errs
+// towards zero -- a bias of ~1e-6 * |a||b| that does not average out over K.  Rounding
+// lo to nearest here makes the residual unbiased (it then shrinks like 1/sqrt(K)).
+__device__ __forceinline__ float split_lo(float v) {
+  const float lo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256)
+split_lo_kernel(const float *__restrict__ x, int64_t ldx, float *__restrict__ lo, int64_t ldlo,
+                int64_t rows, int64_t cols4) {
+  const int64_t total = rows * cols4;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols4, c = (i - r * cols4) << 2;
+    const float4 v = ld_stream(reinterpret_cast<const float4 *>(x + r * ldx + c));
+    float4 o;
+    o.x = split_lo(v.x); o.y = split_lo(v.y); o.z = split_lo(v.z); o.w = split_lo(v.w);
+    *reinterpret_cast<float4 *>(lo + r * ldlo + c) = o;   // re-read soon by TMA: keep in L2
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D tensor map over a matrix stored as `outer` rows of `inner` contiguous elements
+// (row pitch ld elements), box = (box_inner x box_outer), 128-byte swizzle (16-byte atoms,
+// or 32-byte atoms for MN-major fp32 operands), zero OOB fill.
+static int make_map(CUtensorMap *m, const void *base, int es, int64_t inner, int64_t outer, int64_t ld,
+                    int box_inner, int box_outer, bool atom32) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("matmul(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+    return SK_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("matmul(tcgen05): cuTensorMapEncodeTiled failed with %d (inner=%lld outer=%lld ld=%lld box=%dx%d)",
+              (int)r, (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer);
+    return SK_ERR_CUDA;
+  }
+  return SK_OK;
+}
+
+struct Operand {
+  bool mn_major;   // unit stride runs along M/N instead of K
+  int64_t ld;      // pitch (elements) of the non-unit dimension
+};
+
+static bool classify(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, const void *ptr, Operand &o) {
+  if ((((uintptr_t)ptr) & 15) != 0) return false;
+  const int64_t align = 16 / es;   // TMA: base and pitch must be multiples of 16 bytes
+  if (s_k == 1 || k == 1) {        // K-major: `mn` rows of k contiguous elements, pitch s_mn
+    const int64_t ld = mn > 1 ? s_mn : (k + align - 1) / align * align;
+    if (ld % align == 0 && ld >= k) {
+      o.mn_major = false;
+      o.ld = ld;
+      return true;
+    }
+  }
+  if (s_mn == 1 || mn == 1) {      // MN-major: k rows of `mn` contiguous elements, pitch s_k
+    const int64_t ld = k > 1 ? s_k : (mn + align - 1) / align * align;
+    if (ld % align == 0 && ld >= mn) {
+      o.mn_major = true;
+      o.ld = ld;
+      return true;
+    }
+  }
+  return false;
+}
+
+bool tc_supported(const GemmProblem &g, int algo) {
+  const bool bf16 = algo == SK_MM_BF16;
+  if (bf16 != (g.a_dtype == SK_BF16)) return false;
+  if (g.M < 1 || g.N < 1 || g.K < 1) return false;
+  if (g.M > INT32_MAX || g.N > INT32_MAX || g.K > INT32_MAX) return false;
+  Operand a, b;
+  const int es = bf16 ? 2 : 4;
+  if (!classify(g.M, g.K, g.sa_m, g.sa_k, es, g.a, a)) return false;
+  if (!classify(g.N, g.K, g.sb_n, g.sb_k, es, g.b, b)) return false;
+  return encode_fn() != nullptr;
+}
+
+bool tc_profitable(const GemmProblem &g) {
+  // tiny / skinny problems (e.g. the 10-class output layer) stay on the FFMA kernel
+  return g.M >= 64 && g.N >= 64 && g.K >= 32 && (double)g.M * g.N * g.K >= 4.0 * 128 * 128 * 128;
+}
+
+template <int KIND, int BN, int STAGES>
+static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &ob, const float *alo,
+                       int64_t ld_alo, const float *blo, int64_t ld_blo) {
+  constexpr bool BF16 = KIND == KIND_BF16;
+  constexpr bool X3 = KIND == KIND_TF32X3;
+  constexpr int ES = BF16 ? 2 : 4;
+  constexpr int BK = 128 / ES, SLAB = 128 / ES;
+  constexpr size_t STAGE_BYTES = (size_t)(X3 ? 2 : 1) * (BM * 128 + BN * 128);
+  constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  CUtensorMap ma, malo, mb, mblo;
+  int rc;
+  auto mk = [&](CUtensorMap *m, const void *base, int64_t mn, int64_t ld, bool mn_major, int tile_mn) -> int {
+    if (mn_major) return make_map(m, base, ES, mn, g.K, ld, SLAB, BK, !BF16);
+    return make_map(m, base, ES, g.K, mn, ld, BK, tile_mn, false);
+  };
+  if ((rc = mk(&ma, g.a, g.M, oa.ld, oa.mn_major, BM))) return rc;
+  if ((rc = mk(&mb, g.b, g.N, ob.ld, ob.mn_major, BN))) return rc;
+  if (X3) {
+    if ((rc = mk(&malo, alo, g.M, ld_alo, oa.mn_major, BM))) return rc;
+    if ((rc = mk(&mblo, blo, g.N, ld_blo, ob.mn_major, BN))) return rc;
+  } else {
+    malo = ma;
+    mblo = mb;
+  }
+  TcParams p;
+  p.c = g.c; p.bias = g.bias; p.ldc = g.ldc;
+  p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
+  p.epilogue = g.epilogue;
+  p.tiles_m = (int)((g.M + BM - 1) / BM);
+  p.tiles_n = (int)((g.N + BN - 1) / BN);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < ctx().num_sms ? tiles : ctx().num_sms;
+#define LAUNCH(AMN, BMN)                                                                                   \
+  do {                                                                                                     \
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES, AMN, BMN>;                                                \
+    static bool attr_set = false;                                                                          \
+    if (!attr_set) {                                                                                       \
+      SK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));         \
+      attr_set = true;                                                                                     \
+    }                                                                                                      \
+    kern<<<grid, kTcThreads, SMEM, stream()>>>(ma, malo, mb, mblo, p);                                     \
+  } while (0)
+  if (oa.mn_major && ob.mn_major) LAUNCH(true, true);
+  else if (oa.mn_major) LAUNCH(true, false);
+  else if (ob.mn_major) LAUNCH(false, true);
+  else LAUNCH(false, false);
+#undef LAUNCH
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+static int make_lo(const void *src, const Operand &o, int64_t mn, int64_t k, float **lo, int64_t *ld_lo) {
+  // the operand as stored: `outer` rows of `inner` contiguous elements
+  const int64_t inner = o.mn_major ? mn : k, outer = o.mn_major ? k : mn;
+  const int64_t ld = (inner + 3) / 4 * 4;
+  int rc = sk_malloc((size_t)(outer * ld) * sizeof(float), (void **)lo);
+  if (rc) return rc;
+  *ld_lo = ld;
+  const int64_t cols4 = ld / 4;   // reads up to 3 elements past `inner` inside the source pitch (ld <= o.ld)
+  int grid = grid_for(outer * cols4, 256, 8);
+  split_lo_kernel<<<grid, 256, 0, stream()>>>((const float *)src, o.ld, *lo, ld, outer, cols4);
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+int launch_gemm_tc(const GemmProblem &g0, int algo) {
+  GemmProblem g = g0;
+  Operand oa, ob;
+  const int es = algo == SK_MM_BF16 ? 2 : 4;
+  if (!classify(g.M, g.K, g.sa_m, g.sa_k, es, g.a, oa) || !classify(g.N, g.K, g.sb_n, g.sb_k, es, g.b, ob)) {
+    set_error("matmul(tcgen05): unsupported operand layout");
+    return SK_ERR_UNSUPPORTED;
+  }
+  const double flops = 2.0 * (double)g.M * (double)g.N * (double)g.K;
+  for (int64_t bz = 0; bz < g.batch; ++bz) {
+    GemmProblem gi = g;
+    gi.a = (const char *)g.a + bz * g.sa_b * es;
+    gi.b = (const char *)g.b + bz * g.sb_b * es;
+    gi.c = g.c + bz * g.sc_b;
+    int rc;
+    ProfScope ps(SK_PROF_GEMM_TC, flops);
+    if (algo == SK_MM_BF16) {
+      rc = launch_kind<KIND_BF16, 256, 4>(gi, oa, ob, nullptr, 0, nullptr, 0);
+    } else if (algo == SK_MM_TF32) {
+      rc = launch_kind<KIND_TF32, 256, 4>(gi, oa, ob, nullptr, 0, nullptr, 0);
+    } else {
+      float *alo = nullptr, *blo = nullptr;
+      int64_t ld_alo = 0, ld_blo = 0;
+      if ((rc = make_lo(gi.a, oa, g.M, g.K, &alo, &ld_alo))) return rc;
+      if ((rc = make_lo(gi.b, ob, g.N, g.K, &blo, &ld_blo))) { sk_free(alo); return rc; }
+      rc = launch_kind<KIND_TF32X3, 128, 3>(gi, oa, ob, alo, ld_alo, blo, ld_blo);
+      sk_free(alo);   // stream-ordered: reusable only by later work on the same stream
+      sk_free(blo);
+    }
+    if (rc) return rc;
+  }
+  return SK_OK;
+}
+
 }  // namespace sk

@@ -215,6 +215,7 @@ static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, 
                          float *y, float *mean, float *rstd, int64_t R, int C, float eps, int relu) {
   constexpr int RPB = kNT / TPR;
   int grid = grid_for(R, RPB, 8);
+  ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
   ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu);
   SK_LAUNCH_CHECK();
   return SK_OK;
@@ -236,8 +237,11 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
   if (want_params) {
     if ((rc = sk_malloc((size_t)(2 * P * C) * sizeof(float), (void **)&part))) return rc;
   }
-  ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
-                                                     dresidual, part, part ? part + P * C : nullptr, R, C);
+  {
+    ProfScope ps(SK_PROF_LN_BWD, (double)R * C * (12.0 + (mask_mode == 2 ? 4.0 : 0.0) + (dresidual ? 4.0 : 0.0)));
+    ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
+                                                       dresidual, part, part ? part + P * C : nullptr, R, C);
+  }
   SK_LAUNCH_CHECK();
   if (want_params) {
     if (dgamma && (rc = reduce_cols_sum_f32(part, C, dgamma, P, C))) return rc;
@@ -691,6 +695,7 @@ int sk_batchnorm_fwd(const float *x, const float *gamma, const float *beta, floa
   bn_slabs(rows, cols, slabs, rps, col_tiles);
   float *part = nullptr;
   if ((rc = sk_malloc((size_t)(slabs * 2 * cols) * sizeof(float), (void **)&part))) return rc;
+  ProfScope ps(SK_PROF_BN, (double)rows * cols * 12.0);
   bn_stats_kernel<<<dim3((unsigned)col_tiles, (unsigned)slabs), kNT, 0, stream()>>>(x, part, rows, cols, rps);
   note_launch();
   bn_finalize_kernel<<<(unsigned)((cols + kNT - 1) / kNT), kNT, 0, stream()>>>(x, part, slabs, rows, cols, eps, momentum, mean, rstd, running_mean, running_var);
@@ -716,6 +721,7 @@ int sk_batchnorm_bwd(const float *adj, const float *x, const float *gamma, const
   float *part = nullptr;
   if ((rc = sk_malloc((size_t)((slabs * 3 + 3) * cols) * sizeof(float), (void **)&part))) return rc;
   float *coef = part + slabs * 3 * cols;
+  ProfScope ps(SK_PROF_BN, (double)rows * cols * (20.0 + (mask_mode == 2 ? 8.0 : 0.0)));
   bn_bwd_stats_kernel<<<dim3((unsigned)col_tiles, (unsigned)slabs), kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, part, rows, cols, rps);
   note_launch();
   bn_bwd_finalize_kernel<<<(unsigned)((cols + kNT - 1) / kNT), kNT, 0, stream()>>>(part, slabs, rows, cols, gamma, rstd, coef, dgamma, dbeta);
@@ -742,6 +748,7 @@ int sk_softmax_ce_fwd_bwd(const float *logits, const void *labels, int label_dty
   // 1/B is a C double in the reference (backward.pyx:995) that NumPy applies as a float32
   const float inv_b = (float)(1.0 / (double)rows);
   int grid = grid_for(rows, kNT / 32, 8);
+  ProfScope ps(SK_PROF_LOSS, (double)rows * classes * (dlogits ? 8.0 : 4.0));
   softmax_ce_kernel<<<grid, kNT, 0, stream()>>>(logits, labels, label_dtype, rl, dlogits, rows, (int)classes, inv_b);
   SK_LAUNCH_CHECK();
   if (loss) {
@@ -758,6 +765,7 @@ int sk_add_relu(const float *a, const float *b, float *out, int64_t n) {
   SK_REQUIRE(al16(a) && al16(b) && al16(out), "sk_add_relu: pointers must be 16-byte aligned");
   if (n == 0) return SK_OK;
   int grid = grid_for((n + 3) / 4, kNT * 4, 8);
+  ProfScope ps(SK_PROF_EWISE, (double)n * 12.0);
   add_relu_kernel<<<grid, kNT, 0, stream()>>>(a, b, out, n);
   SK_LAUNCH_CHECK();
   return SK_OK;
@@ -770,6 +778,7 @@ int sk_accumulate(float *acc, const float *part, int64_t n) {
   SK_REQUIRE(al16(acc) && al16(part), "sk_accumulate: pointers must be 16-byte aligned");
   if (n == 0) return SK_OK;
   int grid = grid_for((n + 3) / 4, kNT * 4, 8);
+  ProfScope ps(SK_PROF_EWISE, (double)n * 12.0);
   accumulate_kernel<<<grid, kNT, 0, stream()>>>(acc, part, n);
   SK_LAUNCH_CHECK();
   return SK_OK;
@@ -785,6 +794,7 @@ int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float kee
   const float r_keep = (float)(1.0 / (double)keep);
   int grid = grid_for((n + 3) / 4, kNT, 8);
   uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
+  ProfScope ps(SK_PROF_EWISE, (double)n * (mask ? 12.0 : 8.0));
   dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, mask, n, keep, r_keep, seed);
   SK_LAUNCH_CHECK();
   return SK_OK;

@@ -160,6 +160,9 @@ int sk_sgd_step(int n_tensors, float *const *params, const float *const *grads, 
     a.lr = (float)lr; a.wd = (float)weight_decay; a.grad_scale = (float)grad_scale;
     a.have_wd = weight_decay != 0.0; a.have_scale = grad_scale != 1.0;
     if (blocks == 0) continue;
+    double elems = 0;
+    for (int k = 0; k < n; ++k) elems += (double)a.size[k];
+    ProfScope ps(SK_PROF_OPTIM, elems * 12.0);
     sgd_kernel<<<blocks, kOT, 0, stream()>>>(a);
     SK_LAUNCH_CHECK();
   }
@@ -196,6 +199,9 @@ int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
     a.grad_scale = (float)grad_scale;
     a.have_wd = weight_decay != 0.0; a.have_scale = grad_scale != 1.0; a.first = first_step;
     if (blocks == 0) continue;
+    double elems = 0;
+    for (int k = 0; k < n; ++k) elems += (double)a.size[k];
+    ProfScope ps(SK_PROF_OPTIM, elems * (first_step ? 20.0 : 28.0));
     adam_kernel<<<blocks, kOT, 0, stream()>>>(a);
     SK_LAUNCH_CHECK();
   }

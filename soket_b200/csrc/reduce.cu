@@ -494,6 +494,7 @@ int sk_reduce(int op, const sk_array *in, uint32_t axes_mask, sk_array *out) {
         return sk_copy(&src, out);
       }
       if (rs >= 0) {
+        ProfScope ps(SK_PROF_REDUCE, (double)R * C * 4.0);
 #define CALL(OP) launch_rows<OP>(ip, rs, op_, R, C, divisor)
         SK_RED_SWITCH(op, CALL)
 #undef CALL
@@ -502,6 +503,7 @@ int sk_reduce(int op, const sk_array *in, uint32_t axes_mask, sk_array *out) {
     }
     // cols: kept dim has unit stride, one reduced dim with a positive row stride
     if (red.n == 1 && kept.n == 1 && kept.stride[0] == 1 && red.stride[0] >= kept.shape[0]) {
+      ProfScope ps(SK_PROF_REDUCE, (double)red.shape[0] * kept.shape[0] * 4.0);
 #define CALL(OP) launch_cols<OP>(ip, red.stride[0], op_, red.shape[0], kept.shape[0], divisor)
       SK_RED_SWITCH(op, CALL)
 #undef CALL

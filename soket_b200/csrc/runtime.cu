@@ -107,6 +107,35 @@ int ensure_init() {
   return sk_init(0);
 }
 
+// ---- profiler ---------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof[SK_PROF_NUM];
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open[SK_PROF_NUM];
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+bool prof_on() { return g_prof_on; }
+void prof_begin(int family) {
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, ctx().stream);
+  g_prof_open[family] = e;
+}
+void prof_end(int family, double work) {
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, ctx().stream);
+  g_prof[family].push_back({g_prof_open[family], e, work});
+}
+
 static void *g_flush_buf = nullptr;
 static size_t g_flush_bytes = 0;
 
@@ -299,6 +328,34 @@ int sk_flush_l2(void) {
     g_flush_bytes = want;
   }
   SK_CUDA(cudaMemsetAsync(g_flush_buf, 0, g_flush_bytes, ctx().stream));
+  return SK_OK;
+}
+
+// ---- profiler ---
+int sk_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return SK_OK;
+}
+int sk_prof_reset(void) {
+  for (int f = 0; f < SK_PROF_NUM; ++f) {
+    for (auto &r : g_prof[f]) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof[f].clear();
+  }
+  return SK_OK;
+}
+int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *total_work) {
+  SK_REQUIRE(family >= 0 && family < SK_PROF_NUM, "sk_prof_collect: bad family %d", family);
+  if (ctx().ready) SK_CUDA(cudaStreamSynchronize(ctx().stream));
+  double ms = 0, work = 0;
+  for (auto &r : g_prof[family]) {
+    float t = 0;
+    SK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    work += r.work;
+  }
+  if (launches) *launches = (int64_t)g_prof[family].size();
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
   return SK_OK;
 }
 

@@ -20,7 +20,7 @@ def declared_functions():
 
 @pytest.fixture(scope="module")
 def lib():
-    assert os.path.exists(LIB), "libsoketb200.so is not built: python -m soket_b200.build"
+    assert os.path.exists(LIB), "libsoketb200.so is not built: python soket_b200/build.py"
     return ctypes.CDLL(LIB)
 
 

@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 / TMEM / TMA GEMM against NumPy (np.matmul in float64 as the
+exact reference, np.matmul fp32 as the oracle value) for every operand layout the
+reference feeds it (forward.pyx:172-178: x @ w; backward.pyx:720-736: adj @ w.T and
+x.T @ adj on .T VIEWS), ragged / tail shapes included.
+
+Error norm of a dot product: |got - exact| <= tol * (|a| @ |b|).
+  3xTF32 (the fp32 parity path): tol 1e-5 (north_star), typically ~1e-7
+  single-pass TF32: tol 2e-3 (10-bit mantissa; offered for speed, NOT a parity path)
+  bf16 inputs: exact products, fp32 accumulation -> tol 1e-5 against fp32 matmul of the
+  bf16-rounded inputs
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 128, 128), (256, 384, 512), (100, 784, 100), (1000, 100, 260), (129, 33, 257),
+          (64, 64, 64), (2048, 1024, 512), (8, 8, 8), (300, 4, 300), (1, 128, 128), (130, 256, 1)]
+
+
+def err_ratio(got, a, b):
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    bound = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    return (np.abs(got.astype(np.float64) - exact) / np.maximum(bound, 1e-30)).max()
+
+
+def operands(sk, M, K, N, a_t, b_t, seed):
+    """Device operands whose logical shapes are (M,K) and (K,N); *_t builds them as .T views."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-1, 1, (M, K)).astype("float32")
+    b = rng.uniform(-1, 1, (K, N)).astype("float32")
+    da = sk.array(np.ascontiguousarray(a.T)).T if a_t else sk.array(a)
+    db = sk.array(np.ascontiguousarray(b.T)).T if b_t else sk.array(b)
+    assert da.shape == (M, K) and db.shape == (K, N)
+    return a, b, da, db
+
+
+@pytest.mark.parametrize("M,K,N", SHAPES)
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+def test_tf32x3_all_layouts(sk, M, K, N, a_t, b_t):
+    a, b, da, db = operands(sk, M, K, N, a_t, b_t, M + K + N)
+    try:
+        got = sk.asnumpy(sk.matmul(da, db, algo=sk.MM_TF32X3))
+    except RuntimeError as e:
+        # pitches that are not multiples of 16 bytes cannot be described to TMA; the
+        # dispatcher (MM_AUTO) sends those to the FFMA kernel
+        assert "tcgen05 path does not support" in str(e)
+        lda = da.strides[0] if not a_t else da.strides[1]
+        ldb = db.strides[0] if not b_t else db.strides[1]
+        assert lda % 16 != 0 or ldb % 16 != 0
+        got = sk.asnumpy(sk.matmul(da, db))
+    assert got.shape == (M, N) and got.dtype == np.float32
+    assert err_ratio(got, a, b) <= 1e-5
+    ref = np.matmul(a, b, dtype="float32")
+    assert err_ratio(got, a, b) <= max(4 * err_ratio(ref, a, b), 2e-6)
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 384, 512), (132, 36, 260), (1000, 100, 260)])
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+def test_tf32_single_pass(sk, M, K, N, a_t, b_t):
+    a, b, da, db = operands(sk, M, K, N, a_t, b_t, 7)
+    got = sk.asnumpy(sk.matmul(da, db, algo=sk.MM_TF32))
+    assert err_ratio(got, a, b) <= 2e-3
+
+
+def bf16_round(x):
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 384, 512), (136, 40, 264), (1024, 1024, 1024), (64, 64, 64)])
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+def test_bf16(sk, M, K, N, a_t, b_t):
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, (M, K)).astype("float32")
+    b = rng.uniform(-1, 1, (K, N)).astype("float32")
+    ar, br = bf16_round(a), bf16_round(b)
+    da = sk.to_bf16(sk.array(np.ascontiguousarray(a.T))).T if a_t else sk.to_bf16(sk.array(a))
+    db = sk.to_bf16(sk.array(np.ascontiguousarray(b.T))).T if b_t else sk.to_bf16(sk.array(b))
+    assert np.array_equal(sk.asnumpy(da), ar) and np.array_equal(sk.asnumpy(db), br)   # RNE cast is bit-exact
+    got = sk.asnumpy(sk.matmul(da, db))
+    assert err_ratio(got, ar, br) <= 1e-5
+
+
+def test_linear_epilogues_tc(sk):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((512, 784)).astype("float32")
+    w = (rng.standard_normal((784, 256)) * 0.05).astype("float32")
+    bias = rng.standard_normal(256).astype("float32")
+    pre = (x.astype(np.float64) @ w.astype(np.float64) + bias).astype("float32")
+    for relu in (False, True):
+        got = sk.asnumpy(sk.linear(sk.array(x), sk.array(w), sk.array(bias), relu=relu, algo=sk.MM_TF32X3))
+        want = np.maximum(pre, 0) if relu else pre
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(pre).max()
+
+
+def test_auto_dispatch_and_views(sk):
+    """AUTO uses tcgen05 for large problems and the FFMA kernel for small / skinny ones;
+    row-sliced (pitched) operands are consumed in place."""
+    rng = np.random.default_rng(5)
+    big = rng.uniform(-1, 1, (600, 520)).astype("float32")
+    d = sk.array(big)
+    a, da = big[40:552, :512], d[40:552, :512]            # pitched K-major view
+    b, db = big[:512, 8:264], d[:512, 8:264]              # pitched N-major view
+    sk.profile_reset(); sk.profile_enable(True)
+    got = sk.asnumpy(sk.matmul(da, db))
+    fam = sk.profile_collect()
+    sk.profile_enable(False)
+    assert "gemm_tc" in fam and "gemm_simt" not in fam
+    assert err_ratio(got, a, b) <= 1e-5
+    sk.profile_reset(); sk.profile_enable(True)
+    small = sk.asnumpy(sk.matmul(sk.array(big[:100, :100]), sk.array(big[:100, :10])))
+    fam = sk.profile_collect()
+    sk.profile_enable(False)
+    assert "gemm_simt" in fam and "gemm_tc" not in fam
+    assert err_ratio(small, big[:100, :100], big[:100, :10]) <= 1e-5
