@@ -5,7 +5,7 @@
 // MN-major in global memory -- i.e. row-major matrices AND their `.T` views are
 // consumed in place (soket/tensor/ops/forward.pyx:172-178, backward.pyx:720-736).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 64 + 128 * BN/128 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (128B swizzle) into a STAGES-deep
 //               shared-memory ring, completion on `full` mbarriers
 //   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma
@@ -13,7 +13,15 @@
 //               through shared-memory matrix descriptors, fp32 accumulators in TMEM
 //               (2 x BN columns, double buffered); tcgen05.commit releases ring slots
 //               and publishes finished accumulators
-//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 -> registers -> (+bias)(ReLU) -> global
+//   warps 2..   epilogue: tcgen05.ld 32x32b.x32 -> fp32 register accumulators ->
+//               (+bias)(ReLU) -> global
+//
+// Accumulation: the tensor core adds into the fp32 TMEM accumulator with truncation, a
+// bias of ~2^-25 of the running sum per tcgen05.mma that grows LINEARLY with K (measured:
+// 6e-5 relative at K = 8192).  The parity kinds therefore run the K loop in chunks of
+// CHUNK_KB stages; each chunk accumulates in its own TMEM buffer (double buffered) and
+// the epilogue warps drain it into round-to-nearest fp32 REGISTER accumulators
+// ("promotion"), which caps the truncation bias at the chunk length (~1.5e-6).
 //
 // 3xTF32 (fp32 parity at 1e-5): kind::tf32 truncates operands to 10 mantissa bits
 // (~1e-3).  With hi = tf32(x) taken by the hardware from the raw fp32 bits and
@@ -137,10 +145,11 @@ struct TcParams {
 };
 
 constexpr int BM = 128;
-constexpr int kTcThreads = 192;
+// warps: 0 = TMA, 1 = MMA, then 4 epilogue warps per 128 accumulator columns
+constexpr int tc_threads(int bn) { return 64 + 128 * (bn / 128); }
 
-template <int KIND, int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int KIND, int BN, int STAGES, int CHUNK_KB, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(tc_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo,
                const TcParams p) {
@@ -191,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);   // one arrival per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[a]), 4 * (BN / 128));   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,76 +258,98 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);   // epilogue drained this buffer
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
+        for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+          const int kb1 = kb0 + CHUNK_KB < num_kb ? kb0 + CHUNK_KB : num_kb;
+          mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);   // epilogue drained this buffer
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da = make_smem_desc(sbase + k * A_KSTEP, A_LBO, A_SBO, A_LT);
-            const uint64_t db = make_smem_desc(sbase + B_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
-            tc_mma<BF16>(d_tmem, da, db, IDESC, (kb | k) != 0);
-            if (X3) {
-              const uint64_t dalo = make_smem_desc(sbase + A_LO_OFF + k * A_KSTEP, A_LBO, A_SBO, A_LT);
-              const uint64_t dblo = make_smem_desc(sbase + B_LO_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
-              tc_mma<BF16>(d_tmem, da, dblo, IDESC, 1);     // Ahi @ Blo
-              tc_mma<BF16>(d_tmem, dalo, db, IDESC, 1);     // Alo @ Bhi
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t da = make_smem_desc(sbase + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t db = make_smem_desc(sbase + B_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+              tc_mma<BF16>(d_tmem, da, db, IDESC, ((kb - kb0) | k) != 0);
+              if (X3) {
+                const uint64_t dalo = make_smem_desc(sbase + A_LO_OFF + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t dblo = make_smem_desc(sbase + B_LO_OFF + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+                tc_mma<BF16>(d_tmem, da, dblo, IDESC, 1);     // Ahi @ Blo
+                tc_mma<BF16>(d_tmem, dalo, db, IDESC, 1);     // Alo @ Bhi
+              }
             }
+            tc_commit(smem_u32(&empty_bar[stage]));              // slot free once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(smem_u32(&empty_bar[stage]));              // slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(smem_u32(&tfull_bar[acc]));                  // this chunk's partial sums are complete
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));                  // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..) =====================
+    // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and accumulator columns
+    // 128*((w-2)/4)..+128; each thread carries one output row x 128 columns in registers.
+    const int q = warp & 3;
+    const int cbase = ((warp - 2) >> 2) * 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.c) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN;
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      float *crow = p.c + (int64_t)row * p.ldc;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.N) break;           // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        if (row < p.M) {
-          const int col = n0 + c0;
-          const bool full = col + 32 <= p.N;
+      const int m0 = (tile % p.tiles_m) * BM, n0 = (tile / p.tiles_m) * BN + cbase;
+      float accum[128];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]);
-            if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {
-              if (full || col + j < p.N) v += __ldg(p.bias + col + j);
-            }
-            if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
-            r[j] = __float_as_uint(v);
-          }
-          if (full && vec_ok) {
+      for (int j = 0; j < 128; ++j) accum[j] = 0.f;
+      const bool single = num_kb <= CHUNK_KB;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+        if (n0 < p.N) {                      // warp-uniform: this column block exists
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4 *>(crow + col + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-          } else {
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cbase + c0), r);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col + j < p.N) crow[col + j] = __uint_as_float(r[j]);
+              accum[c0 + j] = single ? __uint_as_float(r[j]) : __fadd_rn(accum[c0 + j], __uint_as_float(r[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < p.M && n0 < p.N) {
+        float *crow = p.c + (int64_t)row * p.ldc;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          const int col = n0 + c0;
+          if (col < p.N) {
+            const bool full = col + 32 <= p.N;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = accum[c0 + j];
+              if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {
+                if (full || col + j < p.N) v += __ldg(p.bias + col + j);
+              }
+              if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
+              accum[c0 + j] = v;
+            }
+            if (full && vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(crow + col + j) =
+                    make_float4(accum[c0 + j], accum[c0 + j + 1], accum[c0 + j + 2], accum[c0 + j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.N) crow[col + j] = accum[c0 + j];
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -448,7 +479,7 @@ bool tc_profitable(const GemmProblem &g) {
   return g.M >= 64 && g.N >= 64 && g.K >= 32 && (double)g.M * g.N * g.K >= 4.0 * 128 * 128 * 128;
 }
 
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, int CHUNK_KB>
 static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &ob, const float *alo,
                        int64_t ld_alo, const float *blo, int64_t ld_blo) {
   constexpr bool BF16 = KIND == KIND_BF16;
@@ -482,13 +513,13 @@ static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &o
   const int grid = tiles < ctx().num_sms ? tiles : ctx().num_sms;
 #define LAUNCH(AMN, BMN)                                                                                   \
   do {                                                                                                     \
-    auto kern = gemm_tc_kernel<KIND, BN, STAGES, AMN, BMN>;                                                \
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES, CHUNK_KB, AMN, BMN>;                                                \
     static bool attr_set = false;                                                                          \
     if (!attr_set) {                                                                                       \
       SK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));         \
       attr_set = true;                                                                                     \
     }                                                                                                      \
-    kern<<<grid, kTcThreads, SMEM, stream()>>>(ma, malo, mb, mblo, p);                                     \
+    kern<<<grid, tc_threads(BN), SMEM, stream()>>>(ma, malo, mb, mblo, p);                                     \
   } while (0)
   if (oa.mn_major && ob.mn_major) LAUNCH(true, true);
   else if (oa.mn_major) LAUNCH(true, false);
@@ -530,15 +561,15 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
     int rc;
     ProfScope ps(SK_PROF_GEMM_TC, flops);
     if (algo == SK_MM_BF16) {
-      rc = launch_kind<KIND_BF16, 256, 4>(gi, oa, ob, nullptr, 0, nullptr, 0);
+      rc = launch_kind<KIND_BF16, 256, 4, 8>(gi, oa, ob, nullptr, 0, nullptr, 0);    // promote every K = 512
     } else if (algo == SK_MM_TF32) {
-      rc = launch_kind<KIND_TF32, 256, 4>(gi, oa, ob, nullptr, 0, nullptr, 0);
+      rc = launch_kind<KIND_TF32, 256, 4, 1 << 20>(gi, oa, ob, nullptr, 0, nullptr, 0);  // 1e-3 class: no promotion
     } else {
       float *alo = nullptr, *blo = nullptr;
       int64_t ld_alo = 0, ld_blo = 0;
       if ((rc = make_lo(gi.a, oa, g.M, g.K, &alo, &ld_alo))) return rc;
       if ((rc = make_lo(gi.b, ob, g.N, g.K, &blo, &ld_blo))) { sk_free(alo); return rc; }
-      rc = launch_kind<KIND_TF32X3, 128, 3>(gi, oa, ob, alo, ld_alo, blo, ld_blo);
+      rc = launch_kind<KIND_TF32X3, 128, 3, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);  // promote every K = 128
       sk_free(alo);   // stream-ordered: reusable only by later work on the same stream
       sk_free(blo);
     }

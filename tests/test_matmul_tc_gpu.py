@@ -52,8 +52,7 @@ def test_tf32x3_all_layouts(sk, M, K, N, a_t, b_t):
         got = sk.asnumpy(sk.matmul(da, db))
     assert got.shape == (M, N) and got.dtype == np.float32
     assert err_ratio(got, a, b) <= 1e-5
-    ref = np.matmul(a, b, dtype="float32")
-    assert err_ratio(got, a, b) <= max(4 * err_ratio(ref, a, b), 2e-6)
+    assert err_ratio(got, a, b) <= 2e-6   # typical: a few 1e-7, like an FFMA kernel
 
 
 @pytest.mark.parametrize("M,K,N", [(256, 384, 512), (132, 36, 260), (1000, 100, 260)])
@@ -63,6 +62,29 @@ def test_tf32_single_pass(sk, M, K, N, a_t, b_t):
     a, b, da, db = operands(sk, M, K, N, a_t, b_t, 7)
     got = sk.asnumpy(sk.matmul(da, db, algo=sk.MM_TF32))
     assert err_ratio(got, a, b) <= 2e-3
+
+
+@pytest.mark.parametrize("algo", ["x3", "bf16"])
+@pytest.mark.parametrize("dist", ["uniform", "positive"])
+@pytest.mark.parametrize("M,K,N", [(256, 8192, 256), (512, 16384, 128), (4096, 8192, 512)])
+def test_long_k_accumulation_is_promoted(sk, M, K, N, dist, algo):
+    """The tensor core accumulates into TMEM with truncation (bias ~ K * 2^-25: 6e-5 at
+    K = 8192, measured).  The parity kinds drain TMEM into round-to-nearest fp32 registers
+    every few stages; with that the worst case (all-positive data, long K -- the dW GEMM of
+    the batch-8192 model has K = 8192) stays within 1e-5 of the exact result."""
+    rng = np.random.default_rng(K)
+    lo = -1.0 if dist == "uniform" else 0.0
+    a = rng.uniform(lo, 1, (M, K)).astype("float32")
+    b = rng.uniform(lo, 1, (K, N)).astype("float32")
+    if algo == "bf16":
+        a, b = bf16_round(a), bf16_round(b)
+        got = sk.asnumpy(sk.matmul(sk.to_bf16(sk.array(a)), sk.to_bf16(sk.array(b))))
+    else:
+        got = sk.asnumpy(sk.matmul(sk.array(a), sk.array(b), algo=sk.MM_TF32X3))
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    err = np.abs(got - exact)
+    assert err.max() <= 1e-5 * np.abs(exact).max()
+    assert np.sqrt((err ** 2).mean()) <= 3e-6 * np.sqrt((exact ** 2).mean())
 
 
 def bf16_round(x):
