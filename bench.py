@@ -282,7 +282,9 @@ def run_ours(args, env):
     clocks = ClockSampler(env.local_rank)
     if env.rank == 0:
         clocks.start()
-        time.sleep(1.5)
+        t_wait = time.time()
+        while len(clocks.rows) < 3 and time.time() - t_wait < 15.0:   # NVML is up and polling
+            time.sleep(0.1)
     for _ in range(args.warmup):
         step_resident()
     barrier()

@@ -28,6 +28,59 @@ static int parse_2d(const sk_array *a, const sk_array *b, const sk_array *out, G
   return SK_OK;
 }
 
+static int run_one(const GemmProblem &g0, int algo);
+
+// TMA needs 16-byte aligned bases and row pitches.  Operands that miss that (e.g. the
+// (4096, 10) classifier weight: pitch 40 B) are copied once into a pitch-aligned scratch
+// matrix -- 8 B per element against 2*M*N*K flops -- and the problem re-enters the
+// tensor-core path.  The copy keeps the operand's major-ness.
+static int repitch(const void *src, int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, float **out,
+                   int64_t *o_mn, int64_t *o_k) {
+  const bool k_major = (s_k == 1 || k == 1) && !(s_mn == 1 && mn > 1 && s_k != 1);
+  const int64_t inner = k_major ? k : mn, outer = k_major ? mn : k;
+  const int64_t ld = (inner + 3) / 4 * 4;
+  int rc = sk_malloc((size_t)(outer * ld) * sizeof(float), (void **)out);
+  if (rc) return rc;
+  sk_array s, d;
+  s.data = const_cast<void *>(src); s.dtype = SK_F32; s.ndim = 2;
+  s.shape[0] = outer; s.shape[1] = inner;
+  s.strides[0] = k_major ? s_mn : s_k; s.strides[1] = k_major ? s_k : s_mn;
+  d.data = *out; d.dtype = SK_F32; d.ndim = 2;
+  d.shape[0] = outer; d.shape[1] = inner; d.strides[0] = ld; d.strides[1] = 1;
+  if ((rc = sk_copy(&s, &d))) return rc;
+  *o_mn = k_major ? ld : 1;
+  *o_k = k_major ? 1 : ld;
+  return SK_OK;
+}
+
+static int run_repitched(const GemmProblem &g0) {
+  GemmProblem g = g0;
+  float *ta = nullptr, *tb = nullptr;
+  int rc = SK_OK;
+  for (int64_t bz = 0; bz < g.batch && rc == SK_OK; ++bz) {
+    GemmProblem gi = g;
+    gi.batch = 1;
+    gi.a = (const float *)g.a + bz * g.sa_b;
+    gi.b = (const float *)g.b + bz * g.sb_b;
+    gi.c = g.c + bz * g.sc_b;
+    if (!tc_operand_ok(g.M, g.K, g.sa_m, g.sa_k, 4, gi.a)) {
+      if ((rc = repitch(gi.a, g.M, g.K, g.sa_m, g.sa_k, &ta, &gi.sa_m, &gi.sa_k))) break;
+      gi.a = ta;
+    }
+    if (!tc_operand_ok(g.N, g.K, g.sb_n, g.sb_k, 4, gi.b)) {
+      if ((rc = repitch(gi.b, g.N, g.K, g.sb_n, g.sb_k, &tb, &gi.sb_n, &gi.sb_k))) break;
+      gi.b = tb;
+    }
+    if (tc_supported(gi, SK_MM_TF32X3)) rc = launch_gemm_tc(gi, SK_MM_TF32X3);
+    else rc = run_one(gi, SK_MM_SIMT);
+    if (ta) { sk_free(ta); ta = nullptr; }
+    if (tb) { sk_free(tb); tb = nullptr; }
+  }
+  if (ta) sk_free(ta);
+  if (tb) sk_free(tb);
+  return rc;
+}
+
 static int run_one(const GemmProblem &g0, int algo) {
   GemmProblem g = g0;
   if (g.M == 0 || g.N == 0 || g.batch == 0) return SK_OK;
@@ -47,7 +100,11 @@ static int run_one(const GemmProblem &g0, int algo) {
     return launch_gemm_tc(g, SK_MM_BF16);
   }
   SK_REQUIRE(g.a_dtype == SK_F32 && g.b_dtype == SK_F32, "matmul: operands must be float32 (or bf16)");
-  if (algo == SK_MM_AUTO) algo = tc_supported(g, SK_MM_TF32X3) && tc_profitable(g) ? SK_MM_TF32X3 : SK_MM_SIMT;
+  if (algo == SK_MM_AUTO) {
+    if (!tc_profitable(g)) algo = SK_MM_SIMT;
+    else if (tc_supported(g, SK_MM_TF32X3)) algo = SK_MM_TF32X3;
+    else return run_repitched(g);   // large problem whose row pitch TMA cannot describe
+  }
   if (algo == SK_MM_SIMT) {
     MMArgs p;
     p.a = (const float *)g.a; p.b = (const float *)g.b; p.c = g.c; p.bias = g.bias;

@@ -31,6 +31,8 @@ int launch_gemm_simt(const MMArgs &p);
 
 // tcgen05 path (matmul_tc.cu)
 bool tc_supported(const GemmProblem &g, int algo);
+// one operand: `mn` x `k` elements of `es` bytes with element strides (s_mn, s_k)
+bool tc_operand_ok(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, const void *ptr);
 bool tc_profitable(const GemmProblem &g);
 int launch_gemm_tc(const GemmProblem &g, int algo);
 

@@ -29,121 +29,15 @@
 // Alo@Bhi accumulated in fp32 in TMEM restores ~2^-21 relative accuracy at 1/3 of the
 // TF32 rate.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "matmul.cuh"
+#include "matmul_tc.cuh"
 
 namespace sk {
 
-// ------------------------------------------------------------------ device PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug traps (CUDA error at the next sync) instead of hanging.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool BF16>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if (BF16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (tcgen05 "smem descriptor", SWIZZLE_128B):
-//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte
-//   offset >> 4   [46,48) version = 1 (Blackwell)   [61,64) layout type (2 = 128B swizzle)
-//   layout type 1 = "128B swizzle with 32-byte atoms": the ONLY layout tcgen05 accepts
-//   for MN-major 32-bit (tf32) operands -- 4 K-rows of 128 B per atom, the four 32 B
-//   chunks of a row XOR-ed with (row % 4); TMA writes it with SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-// Instruction descriptor (upper 32 bits of the "runtime idesc"):
-//   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (0 f16, 1 bf16, 2 tf32)
-//   [15] A major (0 K, 1 MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((a_mn ? 1u : 0u) << 15) |
-         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 // ------------------------------------------------------------------ kernel
-enum { KIND_TF32 = 0, KIND_TF32X3 = 1, KIND_BF16 = 2 };
-
-struct TcParams {
-  float *c;
-  const float *bias;
-  int64_t ldc;
-  int M, N, K;
-  int epilogue;
-  int tiles_m, tiles_n;
-};
-
 constexpr int BM = 128;
 // warps: 0 = TMA, 1 = MMA, then 4 epilogue warps per 128 accumulator columns
 constexpr int tc_threads(int bn) { return 64 + 128 * (bn / 128); }
@@ -411,7 +305,7 @@ static EncodeTiledFn encode_fn() {
 // 2-D tensor map over a matrix stored as `outer` rows of `inner` contiguous elements
 // (row pitch ld elements), box = (box_inner x box_outer), 128-byte swizzle (16-byte atoms,
 // or 32-byte atoms for MN-major fp32 operands), zero OOB fill.
-static int make_map(CUtensorMap *m, const void *base, int es, int64_t inner, int64_t outer, int64_t ld,
+int make_map(CUtensorMap *m, const void *base, int es, int64_t inner, int64_t outer, int64_t ld,
                     int box_inner, int box_outer, bool atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
@@ -435,11 +329,6 @@ static int make_map(CUtensorMap *m, const void *base, int es, int64_t inner, int
   return SK_OK;
 }
 
-struct Operand {
-  bool mn_major;   // unit stride runs along M/N instead of K
-  int64_t ld;      // pitch (elements) of the non-unit dimension
-};
-
 static bool classify(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, const void *ptr, Operand &o) {
   if ((((uintptr_t)ptr) & 15) != 0) return false;
   const int64_t align = 16 / es;   // TMA: base and pitch must be multiples of 16 bytes
@@ -462,6 +351,11 @@ static bool classify(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, c
   return false;
 }
 
+bool tc_operand_ok(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, const void *ptr) {
+  Operand o;
+  return classify(mn, k, s_mn, s_k, es, ptr, o);
+}
+
 bool tc_supported(const GemmProblem &g, int algo) {
   const bool bf16 = algo == SK_MM_BF16;
   if (bf16 != (g.a_dtype == SK_BF16)) return false;
@@ -475,8 +369,9 @@ bool tc_supported(const GemmProblem &g, int algo) {
 }
 
 bool tc_profitable(const GemmProblem &g) {
-  // tiny / skinny problems (e.g. the 10-class output layer) stay on the FFMA kernel
-  return g.M >= 64 && g.N >= 64 && g.K >= 32 && (double)g.M * g.N * g.K >= 4.0 * 128 * 128 * 128;
+  // tiny problems (the whole C1 model) stay on the FFMA kernel: one CTA wave of tcgen05
+  // setup costs more than they take.  Skinny ones (N = 10 classifier) do go to tcgen05.
+  return g.K >= 8 && (g.M >= 64 || g.N >= 64) && (double)g.M * g.N * g.K >= 4.0 * 128 * 128 * 128;
 }
 
 template <int KIND, int BN, int STAGES, int CHUNK_KB>
@@ -560,16 +455,24 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
     gi.c = g.c + bz * g.sc_b;
     int rc;
     ProfScope ps(SK_PROF_GEMM_TC, flops);
+    // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one full pair
+    // tile; SOKET_B200_GEMM_2CTA=0 forces the single-CTA kernels.
+    static const int want_2cta = getenv("SOKET_B200_GEMM_2CTA") ? atoi(getenv("SOKET_B200_GEMM_2CTA")) : 1;
+    const bool pair = want_2cta && g.M >= 256 && g.N >= 128;
     if (algo == SK_MM_BF16) {
-      rc = launch_kind<KIND_BF16, 256, 4, 8>(gi, oa, ob, nullptr, 0, nullptr, 0);    // promote every K = 512
+      rc = pair ? launch_gemm_tc2(gi, KIND_BF16, oa, ob, nullptr, 0, nullptr, 0)
+                : launch_kind<KIND_BF16, 256, 4, 8>(gi, oa, ob, nullptr, 0, nullptr, 0);    // promote every K = 512
     } else if (algo == SK_MM_TF32) {
-      rc = launch_kind<KIND_TF32, 256, 4, 1 << 20>(gi, oa, ob, nullptr, 0, nullptr, 0);  // 1e-3 class: no promotion
+      rc = pair ? launch_gemm_tc2(gi, KIND_TF32, oa, ob, nullptr, 0, nullptr, 0)
+                : launch_kind<KIND_TF32, 256, 4, 1 << 20>(gi, oa, ob, nullptr, 0, nullptr, 0);  // 1e-3 class: no promotion
     } else {
       float *alo = nullptr, *blo = nullptr;
       int64_t ld_alo = 0, ld_blo = 0;
       if ((rc = make_lo(gi.a, oa, g.M, g.K, &alo, &ld_alo))) return rc;
       if ((rc = make_lo(gi.b, ob, g.N, g.K, &blo, &ld_blo))) { sk_free(alo); return rc; }
-      rc = launch_kind<KIND_TF32X3, 128, 3, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);  // promote every K = 128
+      if (pair) rc = launch_gemm_tc2(gi, KIND_TF32X3, oa, ob, alo, ld_alo, blo, ld_blo);
+      else if (g.N > 128) rc = launch_kind<KIND_TF32X3, 256, 2, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);
+      else rc = launch_kind<KIND_TF32X3, 128, 3, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);  // promote every K = 128
       sk_free(alo);   // stream-ordered: reusable only by later work on the same stream
       sk_free(blo);
     }

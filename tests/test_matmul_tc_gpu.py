@@ -140,3 +140,19 @@ def test_auto_dispatch_and_views(sk):
     sk.profile_enable(False)
     assert "gemm_simt" in fam and "gemm_tc" not in fam
     assert err_ratio(small, big[:100, :100], big[:100, :10]) <= 1e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(8192, 4096, 10), (4096, 8192, 10), (8192, 10, 4096), (1000, 514, 130)])
+def test_unaligned_pitch_is_repitched_onto_tcgen05(sk, M, K, N):
+    """The 10-class output layer (weight pitch 40 B) and other pitches TMA cannot describe
+    are copied into a 16-byte-pitched scratch and still run on the tensor cores."""
+    rng = np.random.default_rng(M + N)
+    a = rng.uniform(-1, 1, (M, K)).astype("float32")
+    b = rng.uniform(-1, 1, (K, N)).astype("float32")
+    sk.profile_reset(); sk.profile_enable(True)
+    got = sk.asnumpy(sk.matmul(sk.array(a), sk.array(b)))
+    got_t = sk.asnumpy(sk.matmul(sk.array(np.ascontiguousarray(a.T)).T, sk.array(b)))
+    fam = sk.profile_collect()
+    sk.profile_enable(False)
+    assert "gemm_tc" in fam and "gemm_simt" not in fam
+    assert err_ratio(got, a, b) <= 2e-6 and err_ratio(got_t, a, b) <= 2e-6
