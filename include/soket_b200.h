@@ -200,12 +200,14 @@ int sk_rng_bernoulli(sk_array *out, double p);
  * a: (..., M, K)   b: (..., K, N)   out: (..., M, N) contiguous fp32.
  * Operand strides select K-major / MN-major in the tensor-core path; anything
  * else is compacted by the caller first.
- *   SK_MM_AUTO      tcgen05 3xTF32 when shapes allow, else SIMT fp32
+ *   SK_MM_AUTO      tcgen05 fp16x3 (CTA-pair tiles) when shapes allow, else 3xTF32, else SIMT fp32
+ *   SK_MM_F16X3     tcgen05 kind::f16 on fp16 hi/lo splits of the fp32 operands with one
+ *                   power-of-two scale per row of a / column of b (fp32 parity, 2x 3xTF32)
  *   SK_MM_SIMT      CUDA-core fp32 FFMA (exact fp32 products; validation path)
  *   SK_MM_TF32X3    tcgen05 kind::tf32, error-compensated hi/lo split
  *   SK_MM_TF32      tcgen05 kind::tf32 single pass (1e-3 class; not parity)
  *   SK_MM_BF16      tcgen05 kind::f16 on bf16 operands (a,b dtype SK_BF16) */
-typedef enum { SK_MM_AUTO = 0, SK_MM_SIMT = 1, SK_MM_TF32X3 = 2, SK_MM_TF32 = 3, SK_MM_BF16 = 4 } sk_mm_algo;
+typedef enum { SK_MM_AUTO = 0, SK_MM_SIMT = 1, SK_MM_TF32X3 = 2, SK_MM_TF32 = 3, SK_MM_BF16 = 4, SK_MM_F16X3 = 5 } sk_mm_algo;
 typedef enum {
   SK_EPI_NONE = 0,
   SK_EPI_BIAS = 1,      /* + bias[n]                (prototypes.pyx:108-115) */

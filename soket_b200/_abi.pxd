@@ -51,6 +51,7 @@ cdef extern from "soket_b200.h" nogil:
     enum: SK_MM_TF32X3
     enum: SK_MM_TF32
     enum: SK_MM_BF16
+    enum: SK_MM_F16X3
 
     enum: SK_EPI_NONE
     enum: SK_EPI_BIAS

@@ -1179,6 +1179,7 @@ MM_SIMT = SK_MM_SIMT
 MM_TF32X3 = SK_MM_TF32X3
 MM_TF32 = SK_MM_TF32
 MM_BF16 = SK_MM_BF16
+MM_F16X3 = SK_MM_F16X3
 
 
 def set_matmul_algo(int algo):

@@ -4,6 +4,8 @@
 // and the Linear(+ReLU) module sequence prototypes.pyx:108-115,302.
 #include "common.cuh"
 #include "matmul.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace sk {
 
@@ -101,7 +103,10 @@ static int run_one(const GemmProblem &g0, int algo) {
   }
   SK_REQUIRE(g.a_dtype == SK_F32 && g.b_dtype == SK_F32, "matmul: operands must be float32 (or bf16)");
   if (algo == SK_MM_AUTO) {
+    // SOKET_B200_FP32_GEMM = f16x3 (default) | tf32x3 selects the fp32-parity tensor-core scheme
+    static const bool want_f16x3 = !(getenv("SOKET_B200_FP32_GEMM") && !strcmp(getenv("SOKET_B200_FP32_GEMM"), "tf32x3"));
     if (!tc_profitable(g)) algo = SK_MM_SIMT;
+    else if (want_f16x3 && tc_supported(g, SK_MM_F16X3)) algo = SK_MM_F16X3;
     else if (tc_supported(g, SK_MM_TF32X3)) algo = SK_MM_TF32X3;
     else return run_repitched(g);   // large problem whose row pitch TMA cannot describe
   }

@@ -1,0 +1,19 @@
+// matmul_split.cuh -- fp16 hi/lo operand split with K-invariant power-of-two scales.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace sk {
+
+struct SplitOperand {
+  __half *hi = nullptr;        // (outer, ld) fp16, same major-ness as the source
+  __half *lo = nullptr;
+  float *inv_scale = nullptr;  // 2^-e per mn index (exact powers of two)
+  int64_t ld = 0;
+  void release();
+};
+
+int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out);
+
+}  // namespace sk

@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "matmul.cuh"
 #include "matmul_tc.cuh"
+#include "matmul_split.cuh"
 
 namespace sk {
 
@@ -356,7 +357,13 @@ bool tc_operand_ok(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, con
   return classify(mn, k, s_mn, s_k, es, ptr, o);
 }
 
+bool tc_pairable(const GemmProblem &g) {
+  static const int want_2cta = getenv("SOKET_B200_GEMM_2CTA") ? atoi(getenv("SOKET_B200_GEMM_2CTA")) : 1;
+  return want_2cta && g.M >= 256 && g.N >= 128;
+}
+
 bool tc_supported(const GemmProblem &g, int algo) {
+  if (algo == SK_MM_F16X3 && !(tc_pairable(g) && g.K >= 64)) return false;   // CTA-pair kernel only
   const bool bf16 = algo == SK_MM_BF16;
   if (bf16 != (g.a_dtype == SK_BF16)) return false;
   if (g.M < 1 || g.N < 1 || g.K < 1) return false;
@@ -402,6 +409,7 @@ static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &o
   p.c = g.c; p.bias = g.bias; p.ldc = g.ldc;
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
   p.epilogue = g.epilogue;
+  p.row_inv = nullptr; p.col_inv = nullptr;
   p.tiles_m = (int)((g.M + BM - 1) / BM);
   p.tiles_n = (int)((g.N + BN - 1) / BN);
   const int tiles = p.tiles_m * p.tiles_n;
@@ -443,6 +451,10 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
   GemmProblem g = g0;
   Operand oa, ob;
   const int es = algo == SK_MM_BF16 ? 2 : 4;
+  if (algo == SK_MM_F16X3 && !tc_supported(g, algo)) {
+    set_error("matmul(fp16x3): needs M >= 256, N >= 128, K >= 64 and TMA-describable fp32 operands");
+    return SK_ERR_UNSUPPORTED;
+  }
   if (!classify(g.M, g.K, g.sa_m, g.sa_k, es, g.a, oa) || !classify(g.N, g.K, g.sb_n, g.sb_k, es, g.b, ob)) {
     set_error("matmul(tcgen05): unsupported operand layout");
     return SK_ERR_UNSUPPORTED;
@@ -457,9 +469,24 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
     ProfScope ps(SK_PROF_GEMM_TC, flops);
     // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one full pair
     // tile; SOKET_B200_GEMM_2CTA=0 forces the single-CTA kernels.
-    static const int want_2cta = getenv("SOKET_B200_GEMM_2CTA") ? atoi(getenv("SOKET_B200_GEMM_2CTA")) : 1;
-    const bool pair = want_2cta && g.M >= 256 && g.N >= 128;
-    if (algo == SK_MM_BF16) {
+    const bool pair = tc_pairable(g);
+    if (algo == SK_MM_F16X3) {
+      // fp32 operands -> fp16 hi/lo pairs with one power-of-two scale per row of A / column of B
+      SplitOperand sa, sb;
+      const bool a_rows = !oa.mn_major, b_rows = !ob.mn_major;   // K-major: the scale index is the stored row
+      if ((rc = split_f16((const float *)gi.a, oa.ld, a_rows ? g.M : g.K, a_rows ? g.K : g.M, a_rows, sa))) return rc;
+      if ((rc = split_f16((const float *)gi.b, ob.ld, b_rows ? g.N : g.K, b_rows ? g.K : g.N, b_rows, sb))) {
+        sa.release();
+        return rc;
+      }
+      GemmProblem gh = gi;
+      gh.a = sa.hi; gh.b = sb.hi;
+      Operand ha = oa, hb = ob;
+      ha.ld = sa.ld; hb.ld = sb.ld;
+      rc = launch_gemm_tc2(gh, KIND_F16X3, ha, hb, sa.lo, sa.ld, sb.lo, sb.ld, sa.inv_scale, sb.inv_scale);
+      sa.release();   // stream-ordered: reusable only by later work on the same stream
+      sb.release();
+    } else if (algo == SK_MM_BF16) {
       rc = pair ? launch_gemm_tc2(gi, KIND_BF16, oa, ob, nullptr, 0, nullptr, 0)
                 : launch_kind<KIND_BF16, 256, 4, 8>(gi, oa, ob, nullptr, 0, nullptr, 0);    // promote every K = 512
     } else if (algo == SK_MM_TF32) {

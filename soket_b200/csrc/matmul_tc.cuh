@@ -104,7 +104,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn,
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-enum { KIND_TF32 = 0, KIND_TF32X3 = 1, KIND_BF16 = 2 };
+enum { KIND_TF32 = 0, KIND_TF32X3 = 1, KIND_BF16 = 2, KIND_F16X3 = 3 };
+// fp16x3: K blocks (64 elements each) per TMEM accumulation chunk before promotion to registers
+constexpr int F16X3_CHUNK_KB = 4;
 
 struct TcParams {
   float *c;
@@ -113,6 +115,8 @@ struct TcParams {
   int M, N, K;
   int epilogue;
   int tiles_m, tiles_n;
+  const float *row_inv;   // fp16x3: 2^-e per output row / column (operand scales to undo)
+  const float *col_inv;
 };
 
 struct Operand {
@@ -124,7 +128,8 @@ int make_map(CUtensorMap *m, const void *base, int es, int64_t inner, int64_t ou
              int box_inner, int box_outer, bool atom32);
 
 // cta_group::2 kernels (matmul_tc2.cu)
-int launch_gemm_tc2(const GemmProblem &g, int kind, const Operand &oa, const Operand &ob, const float *alo,
-                    int64_t ld_alo, const float *blo, int64_t ld_blo);
+int launch_gemm_tc2(const GemmProblem &g, int kind, const Operand &oa, const Operand &ob, const void *alo,
+                    int64_t ld_alo, const void *blo, int64_t ld_blo, const float *row_inv = nullptr,
+                    const float *col_inv = nullptr);
 
 }  // namespace sk

@@ -84,8 +84,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo,
                 const TcParams p) {
-  constexpr bool BF16 = KIND == KIND_BF16;
-  constexpr bool X3 = KIND == KIND_TF32X3;
+  constexpr bool BF16 = KIND == KIND_BF16 || KIND == KIND_F16X3;   // 16-bit operands (kind::f16)
+  constexpr bool X3 = KIND == KIND_TF32X3 || KIND == KIND_F16X3;   // hi/lo operand pairs, 3 MMAs per K step
   constexpr int ES = BF16 ? 2 : 4;
   constexpr int BK = 128 / ES;
   constexpr int UK = 32 / ES;
@@ -102,7 +102,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr uint32_t A_LT = (A_MN && !BF16) ? 1 : 2, B_LT = (B_MN && !BF16) ? 1 : 2;
   constexpr uint32_t A_KSTEP = A_MN ? UK * 128 : 32;
   constexpr uint32_t B_KSTEP = B_MN ? UK * 128 : 32;
-  constexpr uint32_t IDESC = make_idesc(BF16 ? 1 : 2, A_MN, B_MN, BM2, BN2);
+  constexpr uint32_t IDESC = make_idesc(KIND == KIND_F16X3 ? 0 : (BF16 ? 1 : 2), A_MN, B_MN, BM2, BN2);
   constexpr int TMEM_COLS = 2 * BN2;              // 512: two accumulator buffers
   constexpr int EPI_WARPS = 4 * (BN2 / 128);
 
@@ -261,6 +261,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int row = m0 + q * 32 + lane;
       if (row < p.M && n0 < p.N) {
         float *crow = p.c + (int64_t)row * p.ldc;
+        const float rinv = (KIND == KIND_F16X3) ? __ldg(p.row_inv + row) : 1.f;
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           const int col = n0 + c0;
@@ -269,6 +270,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float v = accum[c0 + j];
+              if (KIND == KIND_F16X3) {
+                // undo the operand scales: exact powers of two, smaller factor first so that the
+                // intermediate cannot overflow when the result itself is representable
+                const float cinv = (full || col + j < p.N) ? __ldg(p.col_inv + col + j) : 1.f;
+                v = (v * fminf(rinv, cinv)) * fmaxf(rinv, cinv);
+              }
               if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {
                 if (full || col + j < p.N) v += __ldg(p.bias + col + j);
               }
@@ -300,10 +307,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 template <int KIND, int STAGES, int CHUNK_KB>
-static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &ob, const float *alo,
-                        int64_t ld_alo, const float *blo, int64_t ld_blo) {
-  constexpr bool BF16 = KIND == KIND_BF16;
-  constexpr bool X3 = KIND == KIND_TF32X3;
+static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &ob, const void *alo,
+                        int64_t ld_alo, const void *blo, int64_t ld_blo, const float *row_inv = nullptr,
+                        const float *col_inv = nullptr) {
+  constexpr bool BF16 = KIND == KIND_BF16 || KIND == KIND_F16X3;
+  constexpr bool X3 = KIND == KIND_TF32X3 || KIND == KIND_F16X3;
   constexpr int ES = BF16 ? 2 : 4;
   constexpr int BK = 128 / ES, SLAB = 128 / ES;
   constexpr size_t STAGE_BYTES = (size_t)(X3 ? 2 : 1) * (BMH * 128 + (BN2 / 2) * 128);
@@ -327,6 +335,7 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   p.c = g.c; p.bias = g.bias; p.ldc = g.ldc;
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
   p.epilogue = g.epilogue;
+  p.row_inv = row_inv; p.col_inv = col_inv;
   p.tiles_m = (int)((g.M + BM2 - 1) / BM2);
   p.tiles_n = (int)((g.N + BN2 - 1) / BN2);
   const int tiles = p.tiles_m * p.tiles_n;
@@ -351,8 +360,14 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   return SK_OK;
 }
 
-int launch_gemm_tc2(const GemmProblem &g, int kind, const Operand &oa, const Operand &ob, const float *alo,
-                    int64_t ld_alo, const float *blo, int64_t ld_blo) {
+int launch_gemm_tc2(const GemmProblem &g, int kind, const Operand &oa, const Operand &ob, const void *alo,
+                    int64_t ld_alo, const void *blo, int64_t ld_blo, const float *row_inv, const float *col_inv) {
+  if (kind == KIND_F16X3) {
+    static const int chunk = getenv("SOKET_B200_F16X3_CHUNK") ? atoi(getenv("SOKET_B200_F16X3_CHUNK")) : F16X3_CHUNK_KB;
+    if (chunk == 1) return launch_kind2<KIND_F16X3, 3, 1>(g, oa, ob, alo, ld_alo, blo, ld_blo, row_inv, col_inv);
+    if (chunk == 2) return launch_kind2<KIND_F16X3, 3, 2>(g, oa, ob, alo, ld_alo, blo, ld_blo, row_inv, col_inv);
+    return launch_kind2<KIND_F16X3, 3, 4>(g, oa, ob, alo, ld_alo, blo, ld_blo, row_inv, col_inv);
+  }
   if (kind == KIND_BF16) return launch_kind2<KIND_BF16, 6, 8>(g, oa, ob, nullptr, 0, nullptr, 0);
   if (kind == KIND_TF32) return launch_kind2<KIND_TF32, 6, 1 << 20>(g, oa, ob, nullptr, 0, nullptr, 0);
   return launch_kind2<KIND_TF32X3, 3, 4>(g, oa, ob, alo, ld_alo, blo, ld_blo);

@@ -156,3 +156,82 @@ def test_unaligned_pitch_is_repitched_onto_tcgen05(sk, M, K, N):
     sk.profile_enable(False)
     assert "gemm_tc" in fam and "gemm_simt" not in fam
     assert err_ratio(got, a, b) <= 2e-6 and err_ratio(got_t, a, b) <= 2e-6
+
+
+# ------------------------------------------------------------------ fp16x3 (the default fp32 path)
+F16_SHAPES = [(256, 64, 128), (256, 384, 512), (512, 784, 256), (1000, 100, 260), (260, 72, 136),
+              (2048, 1024, 512), (384, 8192, 256), (4096, 200, 4096)]
+
+
+@pytest.mark.parametrize("M,K,N", F16_SHAPES)
+@pytest.mark.parametrize("a_t", [False, True])
+@pytest.mark.parametrize("b_t", [False, True])
+def test_f16x3_all_layouts(sk, M, K, N, a_t, b_t):
+    """fp16 hi/lo splits with one power-of-two scale per row of A / column of B, three
+    kind::f16 MMAs per K step: every product is exact in fp32, the dropped lo*lo term is
+    2^-24 relative -- tighter than 3xTF32 at twice its rate."""
+    a, b, da, db = operands(sk, M, K, N, a_t, b_t, M + K + N)
+    got = sk.asnumpy(sk.matmul(da, db, algo=sk.MM_F16X3))
+    assert got.shape == (M, N) and got.dtype == np.float32
+    assert err_ratio(got, a, b) <= 1e-6
+
+
+@pytest.mark.parametrize("dist", ["rows_1e-20..1e20", "lognormal", "positive", "sparse", "constant"])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (True, False), (False, True)])
+def test_f16x3_scaling_handles_dynamic_range(sk, dist, a_t, b_t):
+    """Row / column magnitudes spanning the whole fp32 range, heavy-tailed entries, exact
+    zeros and constant matrices: the K-invariant scales keep the 1e-5 bound per element."""
+    M, K, N = 512, 640, 384
+    rng = np.random.default_rng(42)
+    a = rng.uniform(-1, 1, (M, K))
+    b = rng.uniform(-1, 1, (K, N))
+    if dist == "rows_1e-20..1e20":
+        a *= 10.0 ** rng.uniform(-17, 17, (M, 1))
+        b *= 10.0 ** rng.uniform(-17, 17, (1, N))
+    elif dist == "lognormal":
+        a *= np.exp(rng.normal(0, 2.0, (M, K)))
+        b *= np.exp(rng.normal(0, 2.0, (K, N)))
+    elif dist == "positive":
+        a, b = np.abs(a), np.abs(b)
+    elif dist == "sparse":
+        a *= rng.random((M, K)) < 0.05
+        b *= rng.random((K, N)) < 0.05
+        a[7] = 0.0
+        b[:, 11] = 0.0
+    elif dist == "constant":
+        a[:], b[:] = 0.1, 0.3
+    a, b = a.astype("float32"), b.astype("float32")
+    da = sk.array(np.ascontiguousarray(a.T)).T if a_t else sk.array(a)
+    db = sk.array(np.ascontiguousarray(b.T)).T if b_t else sk.array(b)
+    got = sk.asnumpy(sk.matmul(da, db, algo=sk.MM_F16X3))
+    assert np.isfinite(got).all()
+    assert err_ratio(got, a, b) <= 4e-6
+
+
+def test_f16x3_epilogues_and_auto(sk):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((512, 784)).astype("float32")
+    w = (rng.standard_normal((784, 256)) * 0.05).astype("float32")
+    bias = rng.standard_normal(256).astype("float32")
+    pre = (x.astype(np.float64) @ w.astype(np.float64) + bias).astype("float32")
+    for relu in (False, True):
+        for algo in (sk.MM_F16X3, None):    # None = AUTO, which picks fp16x3 for this shape
+            got = sk.asnumpy(sk.linear(sk.array(x), sk.array(w), sk.array(bias), relu=relu, algo=algo))
+            want = np.maximum(pre, 0) if relu else pre
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(pre).max()
+    with pytest.raises(RuntimeError):       # too small for the CTA-pair kernel: explicit request fails loudly
+        sk.matmul(sk.array(x[:64]), sk.array(w), algo=sk.MM_F16X3)
+
+
+@pytest.mark.parametrize("dist", ["uniform", "positive"])
+@pytest.mark.parametrize("M,K,N", [(256, 8192, 256), (512, 16384, 128), (4096, 8192, 512)])
+def test_f16x3_long_k(sk, M, K, N, dist):
+    rng = np.random.default_rng(K)
+    lo = -1.0 if dist == "uniform" else 0.0
+    a = rng.uniform(lo, 1, (M, K)).astype("float32")
+    b = rng.uniform(lo, 1, (K, N)).astype("float32")
+    got = sk.asnumpy(sk.matmul(sk.array(a), sk.array(b), algo=sk.MM_F16X3))
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    err = np.abs(got - exact)
+    assert err.max() <= 1e-5 * np.abs(exact).max()
+    assert np.sqrt((err ** 2).mean()) <= 3e-6 * np.sqrt((exact ** 2).mean())
