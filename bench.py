@@ -293,14 +293,19 @@ def run_ours(args, env):
     launches0 = sk.launch_count()
     barrier()
     ev0, ev1 = sk.Event(), sk.Event()
+    marks = [sk.Event() for _ in range(args.steps)]
     ev0.record()
     last = None
-    for _ in range(args.steps):
+    for i in range(args.steps):
         last = step_resident()
+        marks[i].record()
     ev1.record()
     ev1.synchronize()
     barrier()
     ms = ev0.elapsed_ms(ev1)
+    per_step = [(ev0 if i == 0 else marks[i - 1]).elapsed_ms(marks[i]) for i in range(args.steps)]
+    print(f"[bench rank {env.rank}] per-step ms (timed region): " + " ".join(f"{t:.2f}" for t in per_step),
+          file=sys.stderr, flush=True)
     launches = sk.launch_count() - launches0
     loss_value = last.item()
 

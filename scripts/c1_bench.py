@@ -1,0 +1,81 @@
+"""BASELINE.json configs[0]: examples/mlp_resnet MLPResNet on MNIST-shaped synthetic data
+(784 -> hidden 100, 3 residual blocks, LayerNorm, batch 100, SGD lr 0.01, dropout 0.01),
+the epoch loop of examples/mlp_resnet/model.py:72-95 (loss.item() every step), on the
+sm_100a backend and on the reference's CPU backend (oracle/_ref) on the host cores.
+
+    python scripts/c1_bench.py [--steps 600] [--variant fn|verbatim]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=600)
+ap.add_argument("--warmup", type=int, default=20)
+ap.add_argument("--variant", default="fn", choices=["fn", "verbatim"])
+ap.add_argument("--no-cpu", action="store_true")
+args = ap.parse_args()
+DIM, HID, NB, C, B = 784, 100, 3, 10, 100
+rng = np.random.default_rng(0)
+X = rng.random((B * 64, DIM), dtype=np.float32)        # 64 distinct batches, cycled
+y = rng.integers(0, C, B * 64).astype(np.uint8)
+
+from oracle import ref_model                            # noqa: E402  (model builder shared with the tests)
+
+
+def run(nn, Tensor, SGD, kaiming, sync, to_dev):
+    np.random.seed(0)
+    model = ref_model.build_model(nn, DIM, HID, NB, C, norm="layer", drop_prob=0.01, retain_fn=args.variant == "fn")
+    for m in model.modules():
+        if type(m).__name__ == "Linear":
+            kaiming(m.weight)
+    opt = SGD(model.parameters(), lr=0.01)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    model.train(True)
+    batches = [(to_dev(X[i * B:(i + 1) * B]), to_dev(y[i * B:(i + 1) * B])) for i in range(64)]
+
+    def step(i):
+        xb, yb = batches[i % 64]
+        loss = crit(model(xb), yb)
+        loss.backward()
+        opt.step()
+        return loss.item()
+    for i in range(args.warmup):
+        step(i)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = step(i)
+    sync()
+    return (time.perf_counter() - t0) / args.steps, last
+
+
+out = {"config": f"MLPResNet(784, 100, 3 blocks, LayerNorm, dropout 0.01), batch 100, SGD lr=0.01, variant={args.variant}",
+       "steps": args.steps}
+import soket_b200 as sk                                 # noqa: E402
+import soket_b200.api as soket                          # noqa: E402
+from soket_b200 import nn as gnn                        # noqa: E402
+from soket_b200.optim import SGD as GSGD                # noqa: E402
+sk.init(0)
+n0 = sk.launch_count()
+sec, loss = run(gnn, soket.Tensor, GSGD, gnn.kaiming_normal, sk.synchronize, lambda a: soket.Tensor(a))
+launches = (sk.launch_count() - n0) / (args.steps + args.warmup)
+out["gpu"] = {"ms_per_step": sec * 1e3, "samples_per_s": B / sec, "launches_per_step": launches, "last_loss": loss}
+if not args.no_cpu:
+    ref = ref_model.import_reference()
+    if ref is not None:
+        import soket.nn as rnn
+        from soket.nn.init import kaiming_normal
+        from soket.optim import SGD as RSGD
+        best = None
+        sec_c, loss_c = run(rnn, ref.Tensor, RSGD, kaiming_normal, lambda: None, lambda a: ref.Tensor(a))
+        out["cpu_reference"] = {"ms_per_step": sec_c * 1e3, "samples_per_s": B / sec_c, "cores": os.cpu_count(),
+                                "last_loss": loss_c, "openblas_threads": os.environ.get("OPENBLAS_NUM_THREADS", "default")}
+        out["speedup"] = sec_c / sec
+print(json.dumps(out), flush=True)

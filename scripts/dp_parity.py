@@ -1,0 +1,96 @@
+"""Data-parallel parity worker (launch under torchrun, one rank per GPU).
+
+Each rank trains the same small MLPResNet on ITS row shard of a seeded global batch for a
+few Adam steps with the NCCL gradient all-reduce of soket_b200.dp; rank 0 then compares
+the parameters with the oracle's W-shard emulation (W forward/backwards on
+the shards, gradients averaged, one optimiser step).  Exit code 0 = parity holds."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import soket_b200 as sk                                   # noqa: E402
+import soket_b200.api as soket                            # noqa: E402
+from soket_b200 import dp, nn                             # noqa: E402
+from soket_b200.optim import SGD, Adam                    # noqa: E402
+from oracle import ref_model, soket_np as O               # noqa: E402   (checker only)
+
+
+def main():
+    env = dp.read_env()
+    sk.init(env.local_rank)
+    rdv = dp.Rendezvous(env)
+    dim, hidden, nb, C, B = 784, 256, 2, 10, 512
+    norm = os.environ.get("DP_NORM", "layer")
+    # SGD is linear in the gradient: strict multi-step comparison.  Adam's first steps are
+    # lr * g / (|g| + eps): elements whose true gradient is zero (every bias in front of a
+    # normalisation layer) turn rounding noise into +-lr updates on BOTH backends, so Adam is
+    # compared after one step on the elements whose gradient is above the noise floor.
+    use_adam = os.environ.get("DP_OPT", "sgd") == "adam"
+    steps = 1 if use_adam else 3
+    rng = np.random.default_rng(0)
+    om = O.MLPResNet(dim, hidden, nb, C, norm=norm)
+    om.init_kaiming(0)
+    for k in om.params:
+        if k.endswith(".W"):
+            om.params[k] = (rng.standard_normal(om.params[k].shape) * np.sqrt(2.0 / om.params[k].shape[0])).astype("float32")
+    model = ref_model.build_model(nn, dim, hidden, nb, C, norm=norm, drop_prob=0.0)
+    named = ref_model.named_parameters(model, nb)
+    for k, t in named.items():
+        # rank 0 holds the real weights, the others garbage: broadcast_parameters must fix that
+        w = om.params[k] if env.rank == 0 else np.full_like(om.params[k], 7.0)
+        t.data = soket.Tensor(w.copy())
+    opt = Adam(model.parameters(), lr=1e-3) if use_adam else SGD(model.parameters(), lr=0.05)
+    ddp = dp.DataParallel(opt, rdv)
+    ddp.broadcast_parameters(0)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    oo = O.Adam(len(om.names()), lr=1e-3) if use_adam else O.SGD(len(om.names()), lr=0.05)
+    start = {k: v.copy() for k, v in om.params.items()}
+    signal = {}
+    sl = dp.shard_rows(B, env.rank, env.world)
+    losses = []
+    for step in range(steps):
+        X = rng.random((B, dim), dtype=np.float32)
+        y = rng.integers(0, C, B).astype(np.uint8)
+        loss = crit(model(soket.Tensor(X[sl])), soket.Tensor(y[sl]))
+        loss.backward()
+        ddp.finish()
+        opt.step()
+        losses.append(loss.item())
+        if env.rank == 0:
+            # oracle: W shards, averaged gradients, one step
+            acc = None
+            shard_losses = []
+            for r in range(env.world):
+                s = dp.shard_rows(B, r, env.world)
+                shard_losses.append(om.loss(om.forward(X[s]), y[s]))
+                g = om.backward()
+                acc = {k: np.asarray(v, dtype=np.float32) / np.float32(env.world) if acc is None
+                       else acc[k] + np.asarray(v, dtype=np.float32) / np.float32(env.world) for k, v in g.items()}
+            names = om.names()
+            signal = {k: np.abs(acc[k]) > 1e-4 * np.abs(acc[k]).max() for k in names}
+            for k, v in zip(names, oo.step([om.params[k] for k in names], [acc[k] for k in names])):
+                om.params[k] = v
+            assert abs(losses[-1] - shard_losses[0]) <= 1e-4 * max(1.0, abs(shard_losses[0])), (step, losses[-1], shard_losses[0])
+    if env.rank == 0:
+        worst = 0.0
+        for k in om.names():
+            got, want = named[k].numpy(), om.params[k]
+            keep = signal[k] if use_adam else np.ones(want.shape, bool)
+            if not keep.any():
+                continue
+            # error of the UPDATE relative to the largest update of that tensor
+            scale = max(float(np.abs(want - start[k]).max()), 1e-30)
+            worst = max(worst, float(np.abs(got - want)[keep].max()) / scale)
+        print(f"dp parity W={env.world} norm={norm} opt={'adam' if use_adam else 'sgd'}: "
+              f"worst update rel err {worst:.2e} over {steps} step(s)", flush=True)
+        assert worst <= 1e-3, worst
+    rdv.barrier()
+    ddp.close()
+
+
+if __name__ == "__main__":
+    main()

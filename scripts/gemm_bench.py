@@ -55,3 +55,15 @@ if '--errors' in sys.argv:
             for K in (512, 4096, 16384):
                 mx, rms = error(512, K, 256, algo, dist)
                 print(f'  err {names[algo]:6s} {dist:8s} K={K:5d}: max {mx:.2e} rms {rms:.2e} (relative to |a|@|b|)', flush=True)
+if '--linear' in sys.argv:
+    for (M, K, N) in [(8192, 4096, 4096), (100, 784, 100)]:
+        x = sk.random.uniform(-1, 1, (M, K), dtype='float32'); w = sk.random.uniform(-1, 1, (K, N), dtype='float32')
+        bias = sk.random.uniform(-1, 1, (N,), dtype='float32')
+        for _ in range(3):
+            sk.linear(x, w, bias, relu=True)
+        e0, e1 = sk.Event(), sk.Event(); e0.record()
+        for _ in range(20):
+            sk.linear(x, w, bias, relu=True)
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_ms(e1) / 20
+        print(f'  fused relu(x@w+b) M{M} K{K} N{N}: {ms:8.4f} ms  {2.0 * M * N * K / ms / 1e9:8.2f} TFLOP/s', flush=True)

@@ -519,6 +519,101 @@ transpose_tiled(const T *__restrict__ src, T *__restrict__ dst, int64_t R, int64
   }
 }
 
+
+// 2-D compaction with contiguous destination rows, 4-byte elements: dst[r, c] =
+// src[r * lds + c * sin] with sin in {0, 1} and any lds (0 = every row the same):
+// materialising broadcast_to views (forward.pyx:120-126; zero strides) and pitched
+// slices.  128-bit stores; TPR (a power of two) threads walk one row, no index division.
+// Algorithmic traffic: 4 B/elem written + the source once.
+template <int SIN>
+__global__ void __launch_bounds__(256)
+copy_rows_u32(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int64_t R, int64_t C,
+              int64_t lds, int64_t ldd, int tpr_log2, int vec_src) {
+  const int tpr = 1 << tpr_log2;
+  const int tx = threadIdx.x & (tpr - 1), ty = threadIdx.x >> tpr_log2;
+  const int rpb = 256 >> tpr_log2;
+  const int64_t C4 = C >> 2;
+  for (int64_t r = (int64_t)blockIdx.x * rpb + ty; r < R; r += (int64_t)gridDim.x * rpb) {
+    const uint32_t *srow = src + r * lds;
+    uint4 *drow = reinterpret_cast<uint4 *>(dst + r * ldd);
+    if (SIN == 0) {
+      const uint32_t v = __ldg(srow);
+      const uint4 v4 = make_uint4(v, v, v, v);
+#pragma unroll 4
+      for (int64_t c4 = tx; c4 < C4; c4 += tpr) drow[c4] = v4;
+    } else if (vec_src) {
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(srow);
+#pragma unroll 4
+      for (int64_t c4 = tx; c4 < C4; c4 += tpr) drow[c4] = __ldg(s4 + c4);
+    } else {
+#pragma unroll 2
+      for (int64_t c4 = tx; c4 < C4; c4 += tpr) {
+        const uint32_t *q = srow + c4 * 4;
+        drow[c4] = make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+      }
+    }
+  }
+}
+
+// 64 x 64 tiled transpose of 4-byte elements with 128-bit global accesses on both sides.
+// dst[r * ldd + c] = src[c * lds + r]  (src unit stride along r, dst along c).
+// Shared tile: 64 "c" rows of 16 uint4 (= 64 r values); the uint4 slot of (c, r) is
+// (r / 4) ^ ((c / 4) & 7), which makes both the 16-byte writes of the load phase and the
+// 4-byte reads of the store phase bank-conflict free.  Requires R, C multiples of 4,
+// lds, ldd multiples of 4 and 16-byte aligned bases (else transpose_tiled).
+__global__ void __launch_bounds__(256)
+transpose64_u32(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int64_t R, int64_t C,
+                int64_t lds, int64_t ldd) {
+  __shared__ uint4 tile[64][16];
+  const int64_t tiles_r = (R + 63) / 64, tiles_c = (C + 63) / 64;
+  const int64_t total = tiles_r * tiles_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // load: half-warp = one source column (16 x uint4 = 64 r); a warp covers 2 columns per j
+  const int r4 = lane & 15, cl0 = warp * 8 + (lane >> 4);
+  uint4 v[4];
+  auto fetch = [&](int64_t t) {
+    const int64_t tc = t / tiles_r, tr = t - tc * tiles_r;
+    const int64_t r = tr * 64 + r4 * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = tc * 64 + cl0 + j * 2;
+      v[j] = (c < C && r < R) ? __ldg(reinterpret_cast<const uint4 *>(src + c * lds + r)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  int64_t t = blockIdx.x;
+  if (t < total) fetch(t);
+  for (; t < total; t += gridDim.x) {
+    const int64_t tc = t / tiles_r, tr = t - tc * tiles_r;
+    const int64_t r0 = tr * 64, c0 = tc * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cl = cl0 + j * 2;
+      tile[cl][r4 ^ ((cl >> 2) & 7)] = v[j];
+    }
+    __syncthreads();
+    // the next tile's loads fly while this one is written out (latency-bound otherwise:
+    // ncu showed 68 % of stall cycles waiting on the global loads at 3.9 TB/s)
+    if (t + gridDim.x < total) fetch(t + gridDim.x);
+    // store: a warp covers 4 consecutive r x 8 uint4 of c (32 c); 2 x 16 such pieces per tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int piece = warp * 4 + j;             // 0..31: (r block of 4) x (c half)
+      const int rl = (piece >> 1) * 4 + (lane & 3);
+      const int c4 = (piece & 1) * 8 + (lane >> 2);
+      const uint32_t *tw = reinterpret_cast<const uint32_t *>(&tile[0][0]);
+      uint32_t e[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cl = c4 * 4 + k;
+        e[k] = tw[(cl * 16 + ((rl >> 2) ^ ((cl >> 2) & 7))) * 4 + (rl & 3)];
+      }
+      const int64_t r = r0 + rl, c = c0 + c4 * 4;
+      if (r < R && c < C) *reinterpret_cast<uint4 *>(dst + r * ldd + c) = make_uint4(e[0], e[1], e[2], e[3]);
+    }
+    __syncthreads();
+  }
+}
+
 // ----------------------------------------------------------------- host side
 static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
@@ -754,10 +849,43 @@ int sk_copy(const sk_array *src, sk_array *dst) {
       note_launch();
       return SK_OK;
     }
+    // contiguous destination rows, source inner stride 0 or 1 (broadcast views, pitched slices)
+    if (esz == 4 && c.ndim <= 2 && c.strides[1][c.ndim - 1] == 1 &&
+        (c.strides[0][c.ndim - 1] == 0 || c.strides[0][c.ndim - 1] == 1) && c.shape[c.ndim - 1] % 4 == 0 &&
+        aligned16(dst->data) && (c.ndim == 1 || c.strides[1][0] % 4 == 0)) {
+      const int64_t R = c.ndim == 2 ? c.shape[0] : 1, C = c.shape[c.ndim - 1];
+      const int64_t lds = c.ndim == 2 ? c.strides[0][0] : 0, ldd = c.ndim == 2 ? c.strides[1][0] : C;
+      const int sin = (int)c.strides[0][c.ndim - 1];
+      const int vec_src = sin == 1 && aligned16(src->data) && lds % 4 == 0;
+      int tpr_log2 = 0;
+      while (tpr_log2 < 8 && (1 << tpr_log2) < C / 4) ++tpr_log2;
+      const int rpb = 256 >> tpr_log2;
+      const int grid = grid_for(R, rpb, 16);
+      ProfScope ps(SK_PROF_COPY, (double)n * 4.0 + (double)(sin ? (lds ? n : C) : R) * 4.0);
+      if (sin == 0) copy_rows_u32<0><<<grid, 256, 0, stream()>>>((const uint32_t *)src->data, (uint32_t *)dst->data, R, C, lds, ldd, tpr_log2, 0);
+      else copy_rows_u32<1><<<grid, 256, 0, stream()>>>((const uint32_t *)src->data, (uint32_t *)dst->data, R, C, lds, ldd, tpr_log2, vec_src);
+      SK_LAUNCH_CHECK();
+      return SK_OK;
+    }
     // 2-D transpose pattern -> shared-memory tiled transpose (coalesced both sides)
     if (c.ndim == 2 && c.strides[0][0] == 1 && c.strides[1][1] == 1 && c.strides[1][0] >= c.shape[1] &&
         c.strides[0][1] >= c.shape[0] && (esz == 4 || esz == 8 || esz == 2 || esz == 1)) {
       int64_t R = c.shape[0], C = c.shape[1];
+      if (esz == 4 && R % 4 == 0 && C % 4 == 0 && c.strides[0][1] % 4 == 0 && c.strides[1][0] % 4 == 0 &&
+          aligned16(src->data) && aligned16(dst->data)) {
+        const int64_t tiles64 = ((R + 63) / 64) * ((C + 63) / 64);
+        static int occ64 = 0;
+        if (!occ64) {
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, transpose64_u32, 256, 0) != cudaSuccess || occ64 < 1) occ64 = 4;
+        }
+        const int64_t cap64 = (int64_t)ctx().num_sms * occ64;   // one resident wave: the tile loop is software-pipelined
+        const int grid64 = (int)(tiles64 < cap64 ? tiles64 : cap64);
+        ProfScope ps(SK_PROF_COPY, (double)n * esz * 2.0);
+        transpose64_u32<<<grid64, 256, 0, stream()>>>((const uint32_t *)src->data, (uint32_t *)dst->data, R, C,
+                                                      c.strides[0][1], c.strides[1][0]);
+        SK_LAUNCH_CHECK();
+        return SK_OK;
+      }
       int64_t tiles = ((R + 31) / 32) * ((C + 31) / 32);
       int grid = (int)(tiles < (int64_t)ctx().num_sms * 16 ? tiles : (int64_t)ctx().num_sms * 16);
       ProfScope ps(SK_PROF_COPY, (double)n * esz * 2.0);

@@ -115,8 +115,100 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const MMArgs p) {
   }
 }
 
+// ------------------------------------------------------------------ small problems
+// The whole config-1 model (batch 100, hidden 100: forward.pyx:172-178 on 100 x 784 x 100
+// and smaller) is ONE 128 x 128 tile for the kernel above -- a single CTA walking K
+// serially (measured 177 us).  Here a CTA owns a 16 x 16 output tile and splits K over 16
+// thread groups (4 x 4 threads x 4 x 4 outputs each); the 16 partial sums are added in a
+// fixed order through shared memory, so the result is deterministic.
+constexpr int ST = 16, SKC = 64, SKL = 16;
+
+template <bool A_KFAST, bool B_NFAST>
+__global__ void __launch_bounds__(256) gemm_small_kernel(const MMArgs p) {
+  __shared__ __align__(16) float As[SKC][ST + 4];
+  __shared__ __align__(16) float Bs[SKC][ST + 4];
+  __shared__ __align__(16) float red[SKL][ST * ST];
+  const int tid = threadIdx.x;
+  const int kl = tid >> 4;            // K lane: owns k = 4*kl .. 4*kl+3 of every 64-wide chunk
+  const int ot = tid & 15;            // output thread: 4 x 4 outputs at (4*oy, 4*ox)
+  const int oy = ot >> 2, ox = ot & 3;
+  const int64_t tiles_n = (p.N + ST - 1) / ST, tiles_m = (p.M + ST - 1) / ST;
+  const int64_t tiles = tiles_m * tiles_n;
+  for (int64_t t = blockIdx.x; t < tiles * p.batch; t += gridDim.x) {
+    const int64_t bz = t / tiles, tt = t - bz * tiles;
+    const int64_t m0 = (tt / tiles_n) * ST, n0 = (tt % tiles_n) * ST;
+    const float *A = p.a + bz * p.sa_b;
+    const float *B = p.b + bz * p.sb_b;
+    float *C = p.c + bz * p.sc_b;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int64_t k0 = 0; k0 < p.K; k0 += SKC) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = tid + e * 256;   // 0..1023 over the 16 x 64 tile
+        int m, k;
+        if (A_KFAST) { k = idx & 63; m = idx >> 6; } else { m = idx & 15; k = idx >> 4; }
+        const int64_t gm = m0 + m, gk = k0 + k;
+        As[k][m] = (gm < p.M && gk < p.K) ? A[gm * p.sa_m + gk * p.sa_k] : 0.f;
+        int n, kb;
+        if (B_NFAST) { n = idx & 15; kb = idx >> 4; } else { kb = idx & 63; n = idx >> 6; }
+        const int64_t gn = n0 + n, gkb = k0 + kb;
+        Bs[kb][n] = (gn < p.N && gkb < p.K) ? B[gkb * p.sb_k + gn * p.sb_n] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = kl * 4 + kk;
+        const float4 a = *reinterpret_cast<const float4 *>(&As[k][oy * 4]);
+        const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][ox * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[kl][(oy * 4 + i) * ST + ox * 4 + j] = acc[i][j];
+    __syncthreads();
+    {
+      float v = red[0][tid];
+#pragma unroll
+      for (int l = 1; l < SKL; ++l) v += red[l][tid];
+      const int64_t gm = m0 + (tid >> 4), gn = n0 + (tid & 15);
+      if (gm < p.M && gn < p.N) {
+        if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) v += p.bias[gn];
+        if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
+        C[gm * p.ldc + gn] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int launch_gemm_simt(const MMArgs &p) {
   if (p.M == 0 || p.N == 0 || p.batch == 0) return SK_OK;
+  const bool a_kfast0 = (p.sa_k == 1) || (p.sa_m != 1);
+  const bool b_nfast0 = (p.sb_n == 1) || (p.sb_k != 1);
+  const int64_t big_tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
+  if (big_tiles < 32) {   // the 128 x 128 kernel would leave most of the 148 SMs idle
+    const int64_t tiles = ((p.M + ST - 1) / ST) * ((p.N + ST - 1) / ST) * p.batch;
+    const int64_t cap = (int64_t)ctx().num_sms * 8;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    ProfScope ps(SK_PROF_GEMM_SIMT, 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch);
+    if (a_kfast0 && b_nfast0) gemm_small_kernel<true, true><<<grid, 256, 0, stream()>>>(p);
+    else if (a_kfast0) gemm_small_kernel<true, false><<<grid, 256, 0, stream()>>>(p);
+    else if (b_nfast0) gemm_small_kernel<false, true><<<grid, 256, 0, stream()>>>(p);
+    else gemm_small_kernel<false, false><<<grid, 256, 0, stream()>>>(p);
+    SK_LAUNCH_CHECK();
+    return SK_OK;
+  }
   const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.batch;
   const int64_t cap = (int64_t)ctx().num_sms * 2;
   const int grid = (int)(tiles < cap ? tiles : cap);

@@ -410,6 +410,7 @@ static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &o
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
   p.epilogue = g.epilogue;
   p.row_inv = nullptr; p.col_inv = nullptr;
+  p.group_m = 1;
   p.tiles_m = (int)((g.M + BM - 1) / BM);
   p.tiles_n = (int)((g.N + BN - 1) / BN);
   const int tiles = p.tiles_m * p.tiles_n;

@@ -115,9 +115,23 @@ struct TcParams {
   int M, N, K;
   int epilogue;
   int tiles_m, tiles_n;
+  int group_m;            // M-tiles per rasterisation group (tile_coords)
   const float *row_inv;   // fp16x3: 2^-e per output row / column (operand scales to undo)
   const float *col_inv;
 };
+
+// Tile rasterisation: groups of `group_m` M-tiles are swept across all N-tiles (M fastest
+// inside the group), so the tiles in flight at any moment share a few A row-blocks and a few
+// B column-blocks that stay L2-resident; the plain M-fastest order re-read A from DRAM once
+// per wave (ncu: 1.05 GB per 8192x4096x4096 launch against 0.2 GB of operands).
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int &tm, int &tn) {
+  const int per_group = group_m * tiles_n;
+  const int g = tile / per_group, within = tile - g * per_group;
+  const int m_base = g * group_m;
+  const int rows = tiles_m - m_base < group_m ? tiles_m - m_base : group_m;
+  tn = within / rows;
+  tm = m_base + (within - tn * rows);
+}
 
 struct Operand {
   bool mn_major;   // unit stride runs along M/N instead of K

@@ -150,8 +150,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile % p.tiles_m) * BM2 + (int)rank * BMH;       // this CTA's A rows
-        const int n0 = (tile / p.tiles_m) * BN2 + (int)rank * BNH;       // this CTA's half of B
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
+        const int m0 = tm * BM2 + (int)rank * BMH;       // this CTA's A rows
+        const int n0 = tn * BN2 + (int)rank * BNH;       // this CTA's half of B
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
@@ -231,8 +233,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.c) & 15) == 0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile % p.tiles_m) * BM2 + (int)rank * BMH;
-      const int n0 = (tile / p.tiles_m) * BN2 + cbase;
+      int tm, tn;
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
+      const int m0 = tm * BM2 + (int)rank * BMH;
+      const int n0 = tn * BN2 + cbase;
       float accum[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) accum[j] = 0.f;
@@ -338,6 +342,8 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   p.row_inv = row_inv; p.col_inv = col_inv;
   p.tiles_m = (int)((g.M + BM2 - 1) / BM2);
   p.tiles_n = (int)((g.N + BN2 - 1) / BN2);
+  static const int group_env = getenv("SOKET_B200_GEMM_GROUP_M") ? atoi(getenv("SOKET_B200_GEMM_GROUP_M")) : 8;
+  p.group_m = group_env < 1 ? 1 : group_env;
   const int tiles = p.tiles_m * p.tiles_n;
   const int max_pairs = ctx().num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;

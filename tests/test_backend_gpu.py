@@ -215,6 +215,38 @@ def test_transpose_compaction_exact(sk, shape, dtype):
     assert_exact(got, np.ascontiguousarray(h.T))
 
 
+@pytest.mark.parametrize("shape", [(4, 4), (64, 64), (68, 132), (100, 784), (784, 100), (1000, 260), (4096, 512)])
+def test_transpose64_and_pitched_sources_exact(sk, shape):
+    """Multiple-of-4 shapes take the 128-bit swizzled 64 x 64 transpose; also from a pitched
+    (column-sliced) parent, and non-multiples fall back to the 32 x 32 kernel -- all bit-exact."""
+    rng = np.random.default_rng(shape[0])
+    h = rng.standard_normal(shape).astype("float32")
+    d = sk.array(h)
+    assert_exact(sk.asnumpy(sk.ascontiguousarray(d.T)), np.ascontiguousarray(h.T))
+    if shape[1] >= 8:
+        assert_exact(sk.asnumpy(sk.ascontiguousarray(d[:, 4:].T)), np.ascontiguousarray(h[:, 4:].T))   # pitched, aligned
+        assert_exact(sk.asnumpy(sk.ascontiguousarray(d[:, 1:-3].T)), np.ascontiguousarray(h[:, 1:-3].T))  # misaligned base
+        assert_exact(sk.asnumpy(sk.ascontiguousarray(d[:, :-1].T)), np.ascontiguousarray(h[:, :-1].T))    # ragged
+
+
+@pytest.mark.parametrize("R,C", [(1, 4), (7, 12), (100, 100), (333, 4096), (2048, 8), (5, 10), (64, 1028)])
+def test_broadcast_and_pitched_row_compaction_exact(sk, R, C):
+    """broadcast_to views (zero strides) and pitched row slices materialise bit-exactly through
+    the vectorised row-copy kernel (C % 4 == 0) or the generic gather (otherwise)."""
+    rng = np.random.default_rng(R * C)
+    row = rng.standard_normal(C).astype("float32")
+    col = rng.standard_normal((R, 1)).astype("float32")
+    big = rng.standard_normal((R + 3, C + 8)).astype("float32")
+    drow, dcol, dbig = sk.array(row), sk.array(col), sk.array(big)
+    assert_exact(sk.asnumpy(sk.ascontiguousarray(sk.broadcast_to(drow, (R, C)))), np.broadcast_to(row, (R, C)))
+    assert_exact(sk.asnumpy(sk.ascontiguousarray(sk.broadcast_to(dcol, (R, C)))), np.broadcast_to(col, (R, C)))
+    assert_exact(sk.asnumpy(sk.ascontiguousarray(sk.broadcast_to(dbig[2:3, 4:4 + C], (R, C)))),
+                 np.broadcast_to(big[2:3, 4:4 + C], (R, C)))
+    for (r0, c0) in ((0, 0), (1, 4), (2, 3)):
+        assert_exact(sk.asnumpy(sk.ascontiguousarray(dbig[r0:r0 + R, c0:c0 + C])), big[r0:r0 + R, c0:c0 + C])
+    assert_exact(sk.asnumpy(sk.ascontiguousarray(sk.broadcast_to(dcol[:, 0], (3, R)))), np.broadcast_to(col[:, 0], (3, R)))
+
+
 def test_astype_matrix(sk):
     rng = np.random.default_rng(8)
     h = (rng.random((17, 9)) * 200 - 50)

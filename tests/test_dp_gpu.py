@@ -1,0 +1,27 @@
+"""Real multi-GPU data-parallel parity: 2 ranks under torchrun, NCCL
+all-reduce of the gradients on the comm stream, against the oracle's W-shard emulation.
+Needs 2 visible B200s (`gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("norm,opt", [("layer", "sgd"), ("batch", "sgd"), ("layer", "adam")])
+def test_two_rank_training_matches_shard_emulation(sk, norm, opt):
+    if sk.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt)
+    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", str(port),
+         os.path.join(ROOT, "scripts", "dp_parity.py")],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "dp parity W=2" in r.stdout

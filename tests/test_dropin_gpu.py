@@ -29,11 +29,22 @@ def test_reference_sees_backend(sk, ref_soket):
 
 @pytest.mark.parametrize("norm", ["layer", "batch"])
 @pytest.mark.parametrize("opt", ["sgd", "adam"])
-def test_reference_mlpresnet_on_backend_matches_cpu(sk, ref_soket, norm, opt):
+@pytest.mark.parametrize("teacher", [False, True])
+def test_reference_mlpresnet_on_backend_matches_cpu(sk, ref_soket, norm, opt, teacher):
+    """The reference's own model / autodiff / optimiser code on soket.gpu() against its CPU
+    device, in lock-step on the same batches.
+
+    teacher=False: free-running for 6 steps, loss within 1e-4.  (Longer free runs measure
+    the chaos of the training dynamics, not the backend: with BatchNorm at batch 100 a
+    1e-7 perturbation -- a different summation order inside one GEMM -- doubles every step
+    and reaches 1e-1 by step 18, on the CPU against itself as well.)
+    teacher=True: 20 steps where the GPU model starts every step from the CPU model's
+    parameters; every step's loss must agree to 1e-5 and the final parameters to 1e-4."""
     soket = ref_soket
     import soket.nn as nn
     from soket.optim import SGD, Adam
-    dim, hidden, nb, C, B, steps = 784, 100, 3, 10, 100, 20
+    dim, hidden, nb, C, B = 784, 100, 3, 10, 100
+    steps = 20 if teacher else 6
     rng = np.random.default_rng(0)
     from oracle import soket_np
     om = soket_np.MLPResNet(dim, hidden, nb, C, norm=norm)
@@ -44,8 +55,7 @@ def test_reference_mlpresnet_on_backend_matches_cpu(sk, ref_soket, norm, opt):
     Xs = rng.random((steps, B, dim), dtype=np.float32)
     ys = rng.integers(0, C, (steps, B)).astype(np.uint8)
 
-    losses = {}
-    finals = {}
+    run = {}
     for devname in ("cpu", "gpu"):
         dev = soket.cpu() if devname == "cpu" else soket.gpu()
         with dev:
@@ -54,20 +64,27 @@ def test_reference_mlpresnet_on_backend_matches_cpu(sk, ref_soket, norm, opt):
             for k, t in named.items():
                 t.data = soket.Tensor(om.params[k].copy(), device=dev)
             o = SGD(model.parameters(), lr=0.01) if opt == "sgd" else Adam(model.parameters(), lr=0.002)
-            crit = nn.SoftmaxCrossEntropyLoss()
-            ls = []
-            for s in range(steps):
-                logits = model(soket.Tensor(Xs[s], device=dev))
-                loss = crit(logits, soket.Tensor(ys[s], device=dev))
+            run[devname] = (dev, model, named, o, nn.SoftmaxCrossEntropyLoss())
+    losses = {"cpu": [], "gpu": []}
+    for s in range(steps):
+        if teacher and s > 0:
+            gdev = run["gpu"][0]
+            for k, t in run["gpu"][2].items():
+                t.data = run["cpu"][2][k].data.to(gdev)
+        for devname in ("cpu", "gpu"):
+            dev, model, named, o, crit = run[devname]
+            with dev:
+                loss = crit(model(soket.Tensor(Xs[s], device=dev)), soket.Tensor(ys[s], device=dev))
                 loss.backward()
                 o.step()
-                ls.append(loss.item())
-            losses[devname] = np.array(ls)
-            finals[devname] = {k: soket.Tensor(t, soket.cpu()) for k, t in named.items()}
-    assert np.all(np.isfinite(losses["gpu"]))
-    assert np.abs(losses["gpu"] - losses["cpu"]).max() <= 1e-4 * max(1.0, np.abs(losses["cpu"]).max())
-    # spot-check final parameters through scalar reductions the reference exposes
-    for k in ("lin0.W", "out.W", "blk0.lin1.W", "blk2.n2.g"):
-        a = (finals["cpu"][k] * finals["cpu"][k]).sum().item()
-        b = (finals["gpu"][k] * finals["gpu"][k]).sum().item()
-        assert abs(a - b) <= 1e-4 * max(abs(a), 1e-12), k
+                losses[devname].append(loss.item())
+    lc, lg = np.array(losses["cpu"]), np.array(losses["gpu"])
+    assert np.all(np.isfinite(lg))
+    tol = 1e-5 if teacher else 1e-4
+    assert np.abs(lg - lc).max() <= tol * max(1.0, np.abs(lc).max()), (lg - lc)
+    if teacher:
+        # spot-check final parameters through scalar reductions the reference exposes
+        for k in ("lin0.W", "out.W", "blk0.lin1.W", "blk2.n2.g"):
+            a = (run["cpu"][2][k] * run["cpu"][2][k]).sum().item()
+            b = (run["gpu"][2][k] * run["gpu"][2][k]).sum().item()
+            assert abs(a - b) <= 1e-4 * max(abs(a), 1e-12), k
