@@ -109,7 +109,8 @@ typedef enum {
   SK_PROF_COPY = 7,
   SK_PROF_BN = 8,
   SK_PROF_LOSS = 9,
-  SK_PROF_NUM = 10
+  SK_PROF_GEMM_PREP = 10, /* operand splits (fp16 hi/lo, tf32 lo) feeding the tcgen05 GEMMs; work = 8 B/elem */
+  SK_PROF_NUM = 11
 } sk_prof_family;
 int sk_prof_enable(int on);
 int sk_prof_reset(void);
@@ -218,6 +219,10 @@ int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo);
 /* fused Linear(+ReLU): out = epi(x @ w + bias). bias may be NULL for EPI_NONE/RELU */
 int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
                   sk_array *out, int epilogue, int algo);
+/* Linear backward (backward.pyx:704-742 for y = x @ w): dx (B,I) = adj (B,O) @ w(I,O).T and
+ * dw (I,O) = x(B,I).T @ adj in one call, so that the fp16x3 path splits adj once for both
+ * GEMMs; falls back to two sk_matmul calls on .T views for other shapes / layouts. */
+int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw);
 /* fp32 -> bf16 (RNE) cast for the bf16 sweep */
 int sk_cast_bf16(const sk_array *src, sk_array *dst);
 

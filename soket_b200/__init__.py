@@ -37,7 +37,7 @@ from ._core import (  # noqa: F401,E402
     exp, log, sqrt, absolute, abs,
     equal, not_equal, greater, greater_equal, less, less_equal,
     sum, mean, max, min, amax, amin, argmax, argmin,
-    matmul, linear, relu_backward, one_hot, set_matmul_algo,
+    matmul, linear, linear_bwd, relu_backward, one_hot, set_matmul_algo,
     MM_AUTO, MM_SIMT, MM_TF32X3, MM_TF32, MM_BF16, MM_F16X3,
     random, device_count, is_available, init, synchronize, launch_count, flush_l2,
     memory_stats, empty_cache, version, Event, Graph, PinnedBuffer,

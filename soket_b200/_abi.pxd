@@ -126,6 +126,7 @@ cdef extern from "soket_b200.h" nogil:
     int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo)
     int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
                       sk_array *out, int epilogue, int algo)
+    int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw)
     int sk_cast_bf16(const sk_array *src, sk_array *dst)
 
     int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta,

@@ -1275,6 +1275,29 @@ def linear(x, w, bias=None, relu=False, algo=None):
     return _matmul_impl(x, w, bias, epi, _DEFAULT_MM_ALGO if algo is None else <int> algo)
 
 
+def linear_bwd(adj, x, w):
+    """Backward of y = x @ w (backward.pyx:704-742): returns (adj @ w.T, x.T @ adj) from one
+    call, so that the fp16x3 path splits `adj` once for both GEMMs."""
+    cdef ndarray a = _as_device(adj)._compact()
+    cdef ndarray xx = _as_device(x)._compact()
+    cdef ndarray ww = _as_device(w)._compact()
+    if a._ndim != 2 or xx._ndim != 2 or ww._ndim != 2:
+        raise ValueError('linear_bwd: operands must be 2-D')
+    if a._code != SK_F32 or xx._code != SK_F32 or ww._code != SK_F32:
+        raise TypeError('linear_bwd: operands must be float32')
+    if xx._shape[0] != a._shape[0] or ww._shape[0] != xx._shape[1] or ww._shape[1] != a._shape[1]:
+        raise ValueError('linear_bwd: shapes must be adj (B,O), x (B,I), w (I,O)')
+    cdef int64_t shp[2]
+    shp[0] = xx._shape[0]; shp[1] = xx._shape[1]
+    cdef ndarray dx = _new_array(2, shp, SK_F32)
+    shp[0] = ww._shape[0]; shp[1] = ww._shape[1]
+    cdef ndarray dw = _new_array(2, shp, SK_F32)
+    cdef sk_array da, dxx, dww, ddx, ddw
+    a._desc(&da); xx._desc(&dxx); ww._desc(&dww); dx._desc(&ddx); dw._desc(&ddw)
+    _check(sk_linear_bwd(&da, &dxx, &dww, &ddx, &ddw))
+    return dx, dw
+
+
 # --------------------------------------------------------------------------- random
 class _Random:
     """`backend.random` namespace (soket/backend/device.pyx:64-66)."""
@@ -1392,7 +1415,7 @@ def flush_l2():
     _check(sk_flush_l2())
 
 
-PROF_FAMILIES = ('gemm_tc', 'gemm_simt', 'ln_fwd', 'ln_bwd', 'ewise', 'reduce', 'optim', 'copy', 'bn', 'loss')
+PROF_FAMILIES = ('gemm_tc', 'gemm_simt', 'ln_fwd', 'ln_bwd', 'ewise', 'reduce', 'optim', 'copy', 'bn', 'loss', 'gemm_prep')
 
 
 def profile_enable(bint on=True):

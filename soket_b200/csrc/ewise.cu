@@ -14,6 +14,7 @@
 //     (bit-exact compaction, casts, comparisons, weak-scalar semantics).
 #include <math.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sk {

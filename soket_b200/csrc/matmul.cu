@@ -198,4 +198,32 @@ int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias, sk
   return matmul_impl(x, w, bias, out, epilogue, algo);
 }
 
+int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(adj && x && w && dx && dw, "sk_linear_bwd: null array");
+  SK_REQUIRE(adj->ndim == 2 && x->ndim == 2 && w->ndim == 2 && dx->ndim == 2 && dw->ndim == 2,
+             "sk_linear_bwd: all operands must be 2-D");
+  const int64_t Bn = adj->shape[0], O = adj->shape[1], I = x->shape[1];
+  SK_REQUIRE(x->shape[0] == Bn && w->shape[0] == I && w->shape[1] == O && dx->shape[0] == Bn && dx->shape[1] == I &&
+                 dw->shape[0] == I && dw->shape[1] == O,
+             "sk_linear_bwd: shapes must be adj (B,O), x (B,I), w (I,O), dx (B,I), dw (I,O)");
+  static const bool want_f16x3 = !(getenv("SOKET_B200_FP32_GEMM") && !strcmp(getenv("SOKET_B200_FP32_GEMM"), "tf32x3"));
+  const sk_array *all[5] = {adj, x, w, dx, dw};
+  bool plain = want_f16x3;
+  for (const sk_array *a : all) plain = plain && a->dtype == SK_F32 && is_contiguous(a);
+  if (plain) {
+    bool done = false;
+    rc = linear_bwd_f16x3((const float *)adj->data, (const float *)x->data, (const float *)w->data,
+                          (float *)dx->data, (float *)dw->data, Bn, I, O, &done);
+    if (rc || done) return rc;
+  }
+  // general path: two GEMMs on .T views (backward.pyx:720-736)
+  sk_array wt = *w, xt = *x;
+  wt.shape[0] = w->shape[1]; wt.shape[1] = w->shape[0]; wt.strides[0] = w->strides[1]; wt.strides[1] = w->strides[0];
+  xt.shape[0] = x->shape[1]; xt.shape[1] = x->shape[0]; xt.strides[0] = x->strides[1]; xt.strides[1] = x->strides[0];
+  if ((rc = matmul_impl(adj, &wt, nullptr, dx, SK_EPI_NONE, SK_MM_AUTO))) return rc;
+  return matmul_impl(&xt, adj, nullptr, dw, SK_EPI_NONE, SK_MM_AUTO);
+}
+
 }  // extern "C"

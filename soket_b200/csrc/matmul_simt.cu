@@ -6,6 +6,7 @@
 // misaligned, e.g. N = 10 classes), and (b) as the on-device cross-check of the
 // tensor-core kernels.  128x128x16 block tile, 8x8 register tile per thread,
 // double-buffered shared memory.
+#include <stdlib.h>
 #include "common.cuh"
 #include "matmul.cuh"
 

@@ -158,8 +158,8 @@ split_rows_long_kernel(const float *__restrict__ x, int64_t ldx, __half *__restr
 // pass 1: column |max| of a (outer x inner) matrix into colmax (uint32 bit patterns of
 // non-negative floats order like the floats: atomicMax is exact and order-independent).
 __global__ void __launch_bounds__(256)
-absmax_cols_kernel(const float *__restrict__ x, int64_t ldx, uint32_t *__restrict__ colmax, int64_t outer,
-                   int64_t inner, int64_t rows_per_slab) {
+absmax_cols_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ row_mul,
+                   uint32_t *__restrict__ colmax, int64_t outer, int64_t inner, int64_t rows_per_slab) {
   __shared__ float sm[8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = ((int64_t)blockIdx.x * 32 + tx) * 4;
@@ -169,15 +169,17 @@ absmax_cols_kernel(const float *__restrict__ x, int64_t ldx, uint32_t *__restric
   if (c + 4 <= inner) {
     for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c));   // read again by the split pass
-      m.x = fmaxf(m.x, fabsf(v.x)); m.y = fmaxf(m.y, fabsf(v.y));
-      m.z = fmaxf(m.z, fabsf(v.z)); m.w = fmaxf(m.w, fabsf(v.w));
+      const float w = row_mul ? fabsf(__ldg(row_mul + r)) : 1.f;
+      m.x = fmaxf(m.x, fabsf(v.x) * w); m.y = fmaxf(m.y, fabsf(v.y) * w);
+      m.z = fmaxf(m.z, fabsf(v.z) * w); m.w = fmaxf(m.w, fabsf(v.w) * w);
     }
   } else if (c < inner) {
     for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float *p = x + r * ldx + c;
-      m.x = fmaxf(m.x, fabsf(p[0]));
-      if (c + 1 < inner) m.y = fmaxf(m.y, fabsf(p[1]));
-      if (c + 2 < inner) m.z = fmaxf(m.z, fabsf(p[2]));
+      const float w = row_mul ? fabsf(__ldg(row_mul + r)) : 1.f;
+      m.x = fmaxf(m.x, fabsf(p[0]) * w);
+      if (c + 1 < inner) m.y = fmaxf(m.y, fabsf(p[1]) * w);
+      if (c + 2 < inner) m.z = fmaxf(m.z, fabsf(p[2]) * w);
     }
   }
   sm[ty][tx * 4 + 0] = m.x; sm[ty][tx * 4 + 1] = m.y; sm[ty][tx * 4 + 2] = m.z; sm[ty][tx * 4 + 3] = m.w;
@@ -193,8 +195,8 @@ absmax_cols_kernel(const float *__restrict__ x, int64_t ldx, uint32_t *__restric
 
 // pass 2: thread = one 8-column unit x a strided set of rows.
 __global__ void __launch_bounds__(256)
-split_cols_kernel(const float *__restrict__ x, int64_t ldx, const uint32_t *__restrict__ colmax,
-                  __half *__restrict__ hi, __half *__restrict__ lo, int64_t ldh, float *__restrict__ inv_scale,
+split_cols_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ row_mul,
+                  const uint32_t *__restrict__ colmax, __half *__restrict__ hi, __half *__restrict__ lo, int64_t ldh, float *__restrict__ inv_scale,
                   int64_t outer, int64_t inner, int64_t rows_per_slab) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t u = (int64_t)blockIdx.x * 32 + tx, c = u * 8;
@@ -223,6 +225,11 @@ split_cols_kernel(const float *__restrict__ x, int64_t ldx, const uint32_t *__re
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = (c + k < inner) ? p[k] : 0.f;
     }
+    if (row_mul) {   // exact: the multipliers are powers of two
+      const float w = __ldg(row_mul + r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= w;
+    }
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -246,7 +253,12 @@ void SplitOperand::release() {
 
 // x: `outer` stored rows of `inner` contiguous fp32 (pitch ldx, 16-byte aligned base and
 // pitch).  scale_rows: one scale per stored row (K-major operand), else per stored column.
-int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out) {
+int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out,
+              const float *row_mul) {
+  if (scale_rows && row_mul) {
+    set_error("split_f16: row multipliers apply to the column-scaled (MN-major) case only");
+    return SK_ERR_ARG;
+  }
   const int64_t ldh = (inner + 7) / 8 * 8;
   const int64_t n_scale = scale_rows ? outer : inner;
   const size_t mat_bytes = ((size_t)(outer * ldh) * sizeof(__half) + 255) / 256 * 256;
@@ -288,7 +300,7 @@ int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool sc
     if (slabs > 65535) slabs = 65535;
     int64_t rps = (outer + slabs - 1) / slabs;
     dim3 g1((unsigned)col_blocks128, (unsigned)((outer + rps - 1) / rps));
-    absmax_cols_kernel<<<g1, 256, 0, stream()>>>(x, ldx, colmax, outer, inner, rps);
+    absmax_cols_kernel<<<g1, 256, 0, stream()>>>(x, ldx, row_mul, colmax, outer, inner, rps);
     SK_LAUNCH_CHECK();
     const int64_t col_blocks256 = (ldh / 8 + 31) / 32;
     slabs = ((int64_t)ctx().num_sms * 8 + col_blocks256 - 1) / col_blocks256;
@@ -297,7 +309,7 @@ int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool sc
     if (slabs > 65535) slabs = 65535;
     rps = (outer + slabs - 1) / slabs;
     dim3 g2((unsigned)col_blocks256, (unsigned)((outer + rps - 1) / rps));
-    split_cols_kernel<<<g2, 256, 0, stream()>>>(x, ldx, colmax, out.hi, out.lo, ldh, out.inv_scale, outer, inner, rps);
+    split_cols_kernel<<<g2, 256, 0, stream()>>>(x, ldx, row_mul, colmax, out.hi, out.lo, ldh, out.inv_scale, outer, inner, rps);
     SK_LAUNCH_CHECK();
   }
   return SK_OK;

@@ -14,6 +14,8 @@ struct SplitOperand {
   void release();
 };
 
-int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out);
+// row_mul (MN-major case only): X[r, :] is multiplied by row_mul[r] (an exact power of two) before the split
+int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out,
+              const float *row_mul = nullptr);
 
 }  // namespace sk

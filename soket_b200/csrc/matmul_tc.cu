@@ -467,46 +467,111 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
     gi.b = (const char *)g.b + bz * g.sb_b * es;
     gi.c = g.c + bz * g.sc_b;
     int rc;
-    ProfScope ps(SK_PROF_GEMM_TC, flops);
-    // CTA pairs (cta_group::2, 256 x 256 tiles) when the problem has at least one full pair
-    // tile; SOKET_B200_GEMM_2CTA=0 forces the single-CTA kernels.
     const bool pair = tc_pairable(g);
+    const double prep_bytes = 8.0 * ((double)g.M * (double)g.K + (double)g.N * (double)g.K);
     if (algo == SK_MM_F16X3) {
       // fp32 operands -> fp16 hi/lo pairs with one power-of-two scale per row of A / column of B
       SplitOperand sa, sb;
       const bool a_rows = !oa.mn_major, b_rows = !ob.mn_major;   // K-major: the scale index is the stored row
-      if ((rc = split_f16((const float *)gi.a, oa.ld, a_rows ? g.M : g.K, a_rows ? g.K : g.M, a_rows, sa))) return rc;
-      if ((rc = split_f16((const float *)gi.b, ob.ld, b_rows ? g.N : g.K, b_rows ? g.K : g.N, b_rows, sb))) {
-        sa.release();
-        return rc;
+      {
+        ProfScope pp(SK_PROF_GEMM_PREP, prep_bytes);
+        if ((rc = split_f16((const float *)gi.a, oa.ld, a_rows ? g.M : g.K, a_rows ? g.K : g.M, a_rows, sa))) return rc;
+        if ((rc = split_f16((const float *)gi.b, ob.ld, b_rows ? g.N : g.K, b_rows ? g.K : g.N, b_rows, sb))) {
+          sa.release();
+          return rc;
+        }
       }
       GemmProblem gh = gi;
       gh.a = sa.hi; gh.b = sb.hi;
       Operand ha = oa, hb = ob;
       ha.ld = sa.ld; hb.ld = sb.ld;
-      rc = launch_gemm_tc2(gh, KIND_F16X3, ha, hb, sa.lo, sa.ld, sb.lo, sb.ld, sa.inv_scale, sb.inv_scale);
+      {
+        ProfScope ps(SK_PROF_GEMM_TC, flops);
+        rc = launch_gemm_tc2(gh, KIND_F16X3, ha, hb, sa.lo, sa.ld, sb.lo, sb.ld, sa.inv_scale, sb.inv_scale);
+      }
       sa.release();   // stream-ordered: reusable only by later work on the same stream
       sb.release();
     } else if (algo == SK_MM_BF16) {
+      ProfScope ps(SK_PROF_GEMM_TC, flops);
       rc = pair ? launch_gemm_tc2(gi, KIND_BF16, oa, ob, nullptr, 0, nullptr, 0)
                 : launch_kind<KIND_BF16, 256, 4, 8>(gi, oa, ob, nullptr, 0, nullptr, 0);    // promote every K = 512
     } else if (algo == SK_MM_TF32) {
+      ProfScope ps(SK_PROF_GEMM_TC, flops);
       rc = pair ? launch_gemm_tc2(gi, KIND_TF32, oa, ob, nullptr, 0, nullptr, 0)
                 : launch_kind<KIND_TF32, 256, 4, 1 << 20>(gi, oa, ob, nullptr, 0, nullptr, 0);  // 1e-3 class: no promotion
     } else {
       float *alo = nullptr, *blo = nullptr;
       int64_t ld_alo = 0, ld_blo = 0;
-      if ((rc = make_lo(gi.a, oa, g.M, g.K, &alo, &ld_alo))) return rc;
-      if ((rc = make_lo(gi.b, ob, g.N, g.K, &blo, &ld_blo))) { sk_free(alo); return rc; }
-      if (pair) rc = launch_gemm_tc2(gi, KIND_TF32X3, oa, ob, alo, ld_alo, blo, ld_blo);
-      else if (g.N > 128) rc = launch_kind<KIND_TF32X3, 256, 2, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);
-      else rc = launch_kind<KIND_TF32X3, 128, 3, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);  // promote every K = 128
+      {
+        ProfScope pp(SK_PROF_GEMM_PREP, prep_bytes);
+        if ((rc = make_lo(gi.a, oa, g.M, g.K, &alo, &ld_alo))) return rc;
+        if ((rc = make_lo(gi.b, ob, g.N, g.K, &blo, &ld_blo))) { sk_free(alo); return rc; }
+      }
+      {
+        ProfScope ps(SK_PROF_GEMM_TC, flops);
+        if (pair) rc = launch_gemm_tc2(gi, KIND_TF32X3, oa, ob, alo, ld_alo, blo, ld_blo);
+        else if (g.N > 128) rc = launch_kind<KIND_TF32X3, 256, 2, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);
+        else rc = launch_kind<KIND_TF32X3, 128, 3, 4>(gi, oa, ob, alo, ld_alo, blo, ld_blo);  // promote every K = 128
+      }
       sk_free(alo);   // stream-ordered: reusable only by later work on the same stream
       sk_free(blo);
     }
     if (rc) return rc;
   }
   return SK_OK;
+}
+
+// Linear backward on SHARED operand splits (prototypes.pyx:108-115 backward = backward.pyx:720-736):
+//   dX (B, I) = adj (B, O) @ W(I, O).T        dW (I, O) = X(B, I).T @ adj (B, O)
+// adj is split ONCE, by rows (scale 2^e_b per sample).  The dX GEMM consumes it as its K-major
+// A operand.  For the dW GEMM the same hi/lo arrays are the MN-major B operand (K = batch);
+// their per-row scale is not constant along K there, so it is folded into the other operand:
+// X'[b, i] = X[b, i] * 2^-e_b (exact), split by columns.  One split pass over adj (12 B/elem
+// for the separate column split) disappears per layer.  All three matrices row-major
+// contiguous, pitches multiples of 16 bytes.  *done = false: shapes not eligible, nothing ran.
+int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx, float *dw, int64_t Bn,
+                     int64_t I, int64_t O, bool *done) {
+  *done = false;
+  GemmProblem gx, gw;
+  memset(&gx, 0, sizeof(gx));
+  memset(&gw, 0, sizeof(gw));
+  gx.a = adj; gx.b = w; gx.c = dx; gx.a_dtype = gx.b_dtype = SK_F32;
+  gx.M = Bn; gx.K = O; gx.N = I; gx.sa_m = O; gx.sa_k = 1; gx.sb_k = 1; gx.sb_n = O; gx.ldc = I; gx.batch = 1;
+  gw.a = x; gw.b = adj; gw.c = dw; gw.a_dtype = gw.b_dtype = SK_F32;
+  gw.M = I; gw.K = Bn; gw.N = O; gw.sa_m = 1; gw.sa_k = I; gw.sb_k = O; gw.sb_n = 1; gw.ldc = O; gw.batch = 1;
+  if (!dx || !dw || !tc_supported(gx, SK_MM_F16X3) || !tc_supported(gw, SK_MM_F16X3)) return SK_OK;
+  int rc;
+  SplitOperand sa, sw, sx;
+  {
+    ProfScope pp(SK_PROF_GEMM_PREP, 8.0 * ((double)Bn * O + (double)I * O + (double)Bn * I));
+    if ((rc = split_f16(adj, O, Bn, O, true, sa))) return rc;
+    if ((rc = split_f16(w, O, I, O, true, sw))) { sa.release(); return rc; }                    // W rows = N index of dX
+    if ((rc = split_f16(x, I, Bn, I, false, sx, sa.inv_scale))) { sa.release(); sw.release(); return rc; }
+  }
+  Operand k_major, mn_major;
+  k_major.mn_major = false;
+  mn_major.mn_major = true;
+  {
+    GemmProblem gh = gx;
+    gh.a = sa.hi; gh.b = sw.hi;
+    Operand oa = k_major, ob = k_major;
+    oa.ld = sa.ld; ob.ld = sw.ld;
+    ProfScope ps(SK_PROF_GEMM_TC, 2.0 * (double)Bn * I * O);
+    rc = launch_gemm_tc2(gh, KIND_F16X3, oa, ob, sa.lo, sa.ld, sw.lo, sw.ld, sa.inv_scale, sw.inv_scale);
+  }
+  if (rc == SK_OK) {
+    GemmProblem gh = gw;
+    gh.a = sx.hi; gh.b = sa.hi;
+    Operand oa = mn_major, ob = mn_major;
+    oa.ld = sx.ld; ob.ld = sa.ld;
+    ProfScope ps(SK_PROF_GEMM_TC, 2.0 * (double)Bn * I * O);
+    rc = launch_gemm_tc2(gh, KIND_F16X3, oa, ob, sx.lo, sx.ld, sa.lo, sa.ld, sx.inv_scale, nullptr);
+  }
+  sa.release();
+  sw.release();
+  sx.release();
+  *done = rc == SK_OK;
+  return rc;
 }
 
 }  // namespace sk

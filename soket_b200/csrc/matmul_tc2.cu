@@ -277,7 +277,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               if (KIND == KIND_F16X3) {
                 // undo the operand scales: exact powers of two, smaller factor first so that the
                 // intermediate cannot overflow when the result itself is representable
-                const float cinv = (full || col + j < p.N) ? __ldg(p.col_inv + col + j) : 1.f;
+                const float cinv = (p.col_inv && (full || col + j < p.N)) ? __ldg(p.col_inv + col + j) : 1.f;
                 v = (v * fminf(rinv, cinv)) * fmaxf(rinv, cinv);
               }
               if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {

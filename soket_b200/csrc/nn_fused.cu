@@ -11,6 +11,7 @@
 // Algorithmic bytes (fp32): LN fwd 8 B/elem, LN bwd 12 B/elem (+4 with a stored
 // ReLU mask), BN fwd 12 B/elem, BN bwd 20 B/elem, CE 8 B/elem, add+relu 12 B/elem.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "reduce.cuh"
@@ -18,6 +19,7 @@
 namespace sk {
 
 constexpr int kNT = 256;
+static inline bool al16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 // sum over a group of TPR threads (32 = one warp, 256 = the whole block);
 // every thread of the group receives the result.
@@ -210,10 +212,354 @@ ln_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ x,
   }
 }
 
+
+// ------------------------------------------------------------------- LayerNorm, staged rows
+// Same arithmetic as ln_fwd_kernel / ln_bwd_kernel for rows longer than 512 columns, with the
+// input rows brought into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier
+// complete_tx) a few rows AHEAD of the row being reduced.  The register-resident kernels are
+// latency bound -- one row per 256-thread block in flight, 120 registers in the backward
+// (ncu: 3.3-3.5 TB/s, 25 % occupancy) -- whereas here the bytes in flight are set by the
+// stage count, not by occupancy.  One block walks rows blockIdx.x, +gridDim.x, ...
+__device__ __forceinline__ uint32_t ln_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ln_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ln_mbar_expect(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ln_mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(ln_smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();   // a protocol bug surfaces as a CUDA error instead of a hang
+}
+__device__ __forceinline__ void ln_bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ln_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(ln_smem_u32(bar)) : "memory");
+}
+
+constexpr int kLnMaxStages = 4;
+constexpr int kLnHeader = 256;   // reduction scratch (2 x 3 x 8 floats) + kLnMaxStages mbarriers
+
+// Block-wide sums of up to three values with ONE __syncthreads: the scratch alternates
+// between two buffers (`buf`), so the next reduction never overwrites values a slower
+// warp is still reading (a warp cannot run two barriers ahead of another).
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float *red, int buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *r = red + buf * 24;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0) r[k * 8 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kNT / 32; ++i) t += r[k * 8 + i];
+    v[k] = t;
+  }
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(kNT, 2)
+ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
+                     const float *__restrict__ gamma, const float *__restrict__ beta,
+                     const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                     const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
+                     float *__restrict__ dresidual, float *__restrict__ part_g,
+                     float *__restrict__ part_b, int64_t R, int C, int stages) {
+  extern __shared__ __align__(128) uint8_t ln_sm[];
+  float *red = reinterpret_cast<float *>(ln_sm);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
+  float *data = reinterpret_cast<float *>(ln_sm + kLnHeader);
+  const int nbuf = mask_mode == 2 ? 3 : 2;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const int t = threadIdx.x;
+  const int C4 = C >> 2;
+  const float inv_n = 1.0f / (float)C;
+  const int64_t n_it = (R - blockIdx.x + gridDim.x - 1) / gridDim.x;   // rows of this block
+
+  auto issue = [&](int64_t it) {   // thread 0 only
+    const int sl = (int)(it % stages);
+    const int64_t row = blockIdx.x + it * gridDim.x;
+    float *dst = data + (size_t)sl * nbuf * C;
+    ln_mbar_expect(&full[sl], row_bytes * nbuf);
+    ln_bulk_load(dst, adj + row * C, row_bytes, &full[sl]);
+    ln_bulk_load(dst + C, x + row * C, row_bytes, &full[sl]);
+    if (nbuf == 3) ln_bulk_load(dst + 2 * C, y_out + row * C, row_bytes, &full[sl]);
+  };
+  if (t == 0) {
+    for (int i = 0; i < stages; ++i) ln_mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int64_t it = 0; it < stages - 1 && it < n_it; ++it) issue(it);
+
+  float4 ag[VPT], ab[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) { ag[j] = make_float4(0.f, 0.f, 0.f, 0.f); ab[j] = ag[j]; }
+
+  for (int64_t it = 0; it < n_it; ++it) {
+    // the slot refilled here was read in iteration it-1, before that iteration's block syncs
+    if (t == 0 && it + stages - 1 < n_it) issue(it + stages - 1);
+    const int sl = (int)(it % stages);
+    const int64_t row = blockIdx.x + it * gridDim.x;
+    const float mean = mean_in[row];
+    const float r = rstd_in[row];
+    ln_mbar_wait(&full[sl], (uint32_t)((it / stages) & 1));
+    const float4 *ar = reinterpret_cast<const float4 *>(data + (size_t)sl * nbuf * C);
+    const float4 *xr = ar + C4;
+    const float4 *yr = ar + 2 * C4;
+    float4 a[VPT], xs[VPT];
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        a[j] = ar[i];
+        xs[j] = xr[i];
+        xs[j].x -= mean; xs[j].y -= mean; xs[j].z -= mean; xs[j].w -= mean;
+        float4 g = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (mask_mode == 1) {
+          float4 b = beta ? __ldg(reinterpret_cast<const float4 *>(beta) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(affine(xs[j].x, r, g.x, b.x) > 0.f)) a[j].x = 0.f;
+          if (!(affine(xs[j].y, r, g.y, b.y) > 0.f)) a[j].y = 0.f;
+          if (!(affine(xs[j].z, r, g.z, b.z) > 0.f)) a[j].z = 0.f;
+          if (!(affine(xs[j].w, r, g.w, b.w) > 0.f)) a[j].w = 0.f;
+        } else if (mask_mode == 2) {
+          const float4 yo = yr[i];
+          if (!(yo.x > 0.f)) a[j].x = 0.f;
+          if (!(yo.y > 0.f)) a[j].y = 0.f;
+          if (!(yo.z > 0.f)) a[j].z = 0.f;
+          if (!(yo.w > 0.f)) a[j].w = 0.f;
+        }
+        if (dresidual) st_stream(reinterpret_cast<float4 *>(dresidual + row * C) + i, a[j]);
+        // dgamma += norm * adj ; dbeta += adj   (backward.pyx:1058-1078)
+        ag[j].x += (xs[j].x * r) * a[j].x; ag[j].y += (xs[j].y * r) * a[j].y;
+        ag[j].z += (xs[j].z * r) * a[j].z; ag[j].w += (xs[j].w * r) * a[j].w;
+        ab[j].x += a[j].x; ab[j].y += a[j].y; ab[j].z += a[j].z; ab[j].w += a[j].w;
+        a[j].x *= g.x; a[j].y *= g.y; a[j].z *= g.z; a[j].w *= g.w;
+        s1 += (a[j].x * xs[j].x + a[j].y * xs[j].y) + (a[j].z * xs[j].z + a[j].w * xs[j].w);
+        s2 += (a[j].x + a[j].y) + (a[j].z + a[j].w);
+        s3 += (xs[j].x + xs[j].y) + (xs[j].z + xs[j].w);
+      } else {
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xs[j] = a[j];
+      }
+    }
+    float sums[3] = {s1, s2, s3};
+    block_sum_n<3>(sums, red, (int)(it & 1));
+    s1 = sums[0]; s2 = sums[1]; s3 = sums[2];
+    // backward.pyx:1094-1126
+    const float dvar = s1 * (-0.5f * ((r * r) * r));
+    const float dmean = (-r) * s2 + dvar * (inv_n * (-2.0f * s3));
+    const float c0 = inv_n * dmean;
+    const float c2 = dvar * (2.0f * inv_n);
+    float4 *dr = reinterpret_cast<float4 *>(dx + row * C);
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        float4 o;
+        o.x = c0 + (a[j].x * r + c2 * xs[j].x); o.y = c0 + (a[j].y * r + c2 * xs[j].y);
+        o.z = c0 + (a[j].z * r + c2 * xs[j].z); o.w = c0 + (a[j].w * r + c2 * xs[j].w);
+        st_stream(dr + i, o);
+      }
+    }
+  }
+  if (part_g) {
+    const int64_t prow = blockIdx.x;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        reinterpret_cast<float4 *>(part_g + prow * C)[i] = ag[j];
+        reinterpret_cast<float4 *>(part_b + prow * C)[i] = ab[j];
+      }
+    }
+  }
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(kNT, 2)
+ln_fwd_staged_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, const float *__restrict__ residual,
+                     float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                     int64_t R, int C, float eps, int relu, int stages) {
+  extern __shared__ __align__(128) uint8_t ln_sm[];
+  float *red = reinterpret_cast<float *>(ln_sm);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
+  float *data = reinterpret_cast<float *>(ln_sm + kLnHeader);
+  const int nbuf = residual ? 2 : 1;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  const int t = threadIdx.x;
+  const int C4 = C >> 2;
+  const float n_obs = (float)C;
+  const int64_t n_it = (R - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto issue = [&](int64_t it) {
+    const int sl = (int)(it % stages);
+    const int64_t row = blockIdx.x + it * gridDim.x;
+    float *dst = data + (size_t)sl * nbuf * C;
+    ln_mbar_expect(&full[sl], row_bytes * nbuf);
+    ln_bulk_load(dst, x + row * C, row_bytes, &full[sl]);
+    if (nbuf == 2) ln_bulk_load(dst + C, residual + row * C, row_bytes, &full[sl]);
+  };
+  if (t == 0) {
+    for (int i = 0; i < stages; ++i) ln_mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int64_t it = 0; it < stages - 1 && it < n_it; ++it) issue(it);
+  for (int64_t it = 0; it < n_it; ++it) {
+    if (t == 0 && it + stages - 1 < n_it) issue(it + stages - 1);
+    const int sl = (int)(it % stages);
+    const int64_t row = blockIdx.x + it * gridDim.x;
+    ln_mbar_wait(&full[sl], (uint32_t)((it / stages) & 1));
+    const float4 *xr = reinterpret_cast<const float4 *>(data + (size_t)sl * nbuf * C);
+    const float4 *rr = xr + C4;
+    float4 v[VPT], rs[VPT];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        v[j] = xr[i];
+        if (nbuf == 2) rs[j] = rr[i];
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      } else {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float s_[1] = {s};
+    block_sum_n<1>(s_, red, 0);
+    const float mean = s_[0] / n_obs;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+      }
+    }
+    float q_[1] = {q};
+    block_sum_n<1>(q_, red, 1);
+    const float var = q_[0] / n_obs;
+    const float r = 1.0f / sqrtf(var + eps);
+    if (t == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = r;
+    }
+    float4 *yr = reinterpret_cast<float4 *>(y + row * C);
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = t + j * kNT;
+      if (i < C4) {
+        float4 g = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 b = beta ? __ldg(reinterpret_cast<const float4 *>(beta) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = affine(v[j].x, r, g.x, b.x); o.y = affine(v[j].y, r, g.y, b.y);
+        o.z = affine(v[j].z, r, g.z, b.z); o.w = affine(v[j].w, r, g.w, b.w);
+        if (nbuf == 2) {
+          o.x = __fadd_rn(rs[j].x, o.x); o.y = __fadd_rn(rs[j].y, o.y);
+          o.z = __fadd_rn(rs[j].z, o.z); o.w = __fadd_rn(rs[j].w, o.w);
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        st_stream(yr + i, o);
+      }
+    }
+  }
+}
+
+// stage count / blocks per SM for the staged kernels; stages == 0: use the register kernels
+static void ln_stage_plan(int nbuf, int C, int &stages, int &blocks_per_sm, size_t &smem, int max_blocks = 2) {
+  static const int off = getenv("SOKET_B200_LN_STAGED") ? !atoi(getenv("SOKET_B200_LN_STAGED")) : 0;
+  const size_t stage_bytes = (size_t)nbuf * C * 4;
+  stages = 0;
+  if (off || C <= 512) return;
+  const size_t budget2 = 100 * 1024, budget1 = 200 * 1024, budget3 = 66 * 1024;
+  if (max_blocks >= 3 && stage_bytes * 3 + kLnHeader <= budget3) {
+    blocks_per_sm = 3;
+    stages = (int)((budget3 - kLnHeader) / stage_bytes);
+  } else if (stage_bytes * 2 + kLnHeader <= budget2) {
+    blocks_per_sm = 2;
+    stages = (int)((budget2 - kLnHeader) / stage_bytes);
+  } else if (stage_bytes * 2 + kLnHeader <= budget1) {
+    blocks_per_sm = 1;
+    stages = (int)((budget1 - kLnHeader) / stage_bytes);
+  } else {
+    return;
+  }
+  if (stages > kLnMaxStages) stages = kLnMaxStages;
+  smem = stages * stage_bytes + kLnHeader;
+}
+
+
+// dgamma / dbeta from the per-block partial rows of the LayerNorm backward: ONE launch
+// column-sums both (P x C) matrices (they are L2 resident: just written).  Block = 8 float4
+// column groups x 32 row lanes; the 32 lane sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(kNT)
+ln_param_grads_kernel(const float *__restrict__ part_g, const float *__restrict__ part_b,
+                      float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t P, int C) {
+  __shared__ float4 sm[32][8];
+  const float *part = blockIdx.y == 0 ? part_g : part_b;
+  float *out = blockIdx.y == 0 ? dgamma : dbeta;
+  if (out == nullptr) return;
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c = (blockIdx.x * 8 + cg) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (int64_t r = rl; r < P; r += 32) {
+      const float4 v = *reinterpret_cast<const float4 *>(part + r * C + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sm[rl][cg] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x >> 2, k = threadIdx.x & 3;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += reinterpret_cast<const float *>(&sm[i][g])[k];
+    const int cc = (blockIdx.x * 8 + g) * 4 + k;
+    if (cc < C) out[cc] = t;
+  }
+}
+
 template <int TPR, int VPT>
 static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, const float *residual,
                          float *y, float *mean, float *rstd, int64_t R, int C, float eps, int relu) {
   constexpr int RPB = kNT / TPR;
+  if (TPR == kNT) {
+    int stages, bps = 1;
+    size_t smem = 0;
+    ln_stage_plan(residual ? 2 : 1, C, stages, bps, smem, VPT <= 4 ? 3 : 2);
+    if (stages >= 2) {
+      auto kern = ln_fwd_staged_kernel<VPT>;
+      static bool attr_set = false;
+      if (!attr_set) {
+        SK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kLnHeader));
+        attr_set = true;
+      }
+      const int64_t cap = (int64_t)ctx().num_sms * bps;
+      const int grid = (int)(R < cap ? R : cap);
+      ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
+      kern<<<grid, kNT, smem, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, stages);
+      SK_LAUNCH_CHECK();
+      return SK_OK;
+    }
+  }
   int grid = grid_for(R, RPB, 8);
   ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
   ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu);
@@ -229,6 +575,10 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
   // persistent: each group walks many rows so the dgamma/dbeta partial matrix stays small
   int64_t need = (R + RPB - 1) / RPB;
   int64_t cap = (int64_t)ctx().num_sms * (TPR == 32 ? 4 : 2);
+  int stages = 0, bps = 1;
+  size_t smem = 0;
+  if (TPR == kNT && al16(adj) && al16(x) && (mask_mode != 2 || al16(y_out))) ln_stage_plan(mask_mode == 2 ? 3 : 2, C, stages, bps, smem);
+  if (stages >= 2) cap = (int64_t)ctx().num_sms * bps;
   int grid = (int)(need < cap ? need : cap);
   float *part = nullptr;
   const int64_t P = (int64_t)grid * RPB;
@@ -239,13 +589,25 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
   }
   {
     ProfScope ps(SK_PROF_LN_BWD, (double)R * C * (12.0 + (mask_mode == 2 ? 4.0 : 0.0) + (dresidual ? 4.0 : 0.0)));
-    ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
-                                                       dresidual, part, part ? part + P * C : nullptr, R, C);
+    if (stages >= 2) {
+      auto kern = ln_bwd_staged_kernel<VPT>;
+      static bool attr_set = false;
+      if (!attr_set) {
+        SK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kLnHeader));
+        attr_set = true;
+      }
+      kern<<<grid, kNT, smem, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, part,
+                                          part ? part + P * C : nullptr, R, C, stages);
+    } else {
+      ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
+                                                         dresidual, part, part ? part + P * C : nullptr, R, C);
+    }
   }
   SK_LAUNCH_CHECK();
   if (want_params) {
-    if (dgamma && (rc = reduce_cols_sum_f32(part, C, dgamma, P, C))) return rc;
-    if (dbeta && (rc = reduce_cols_sum_f32(part + P * C, C, dbeta, P, C))) return rc;
+    dim3 pg((unsigned)((C / 4 + 7) / 8), 2);
+    ln_param_grads_kernel<<<pg, kNT, 0, stream()>>>(part, part + P * C, dgamma, dbeta, P, C);
+    SK_LAUNCH_CHECK();
     return sk_free(part);
   }
   return SK_OK;
@@ -639,7 +1001,6 @@ colsum_mask_kernel(const float *__restrict__ adj, const float *__restrict__ y_ou
 static uint64_t g_dropout_seed = 0x0d15ea5e;
 static uint64_t g_dropout_calls = 0;
 
-static inline bool al16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace sk
 

@@ -1046,11 +1046,16 @@ class _LinearOp(Op):
         a2 = adj if adj.ndim == 2 else B.reshape(adj, (-1, adj.shape[-1]))
         x2 = x._data if x._data.ndim == 2 else B.reshape(x._data, (-1, x.shape[-1]))
         gx = None
-        if x.requires_grad:
-            gx = B.matmul(a2, w._data.T)
+        if x.requires_grad and w.requires_grad:
+            gx, gw = B.linear_bwd(a2, x2, w._data)     # one split of adj shared by both GEMMs
             if x._data.ndim != 2:
                 gx = B.reshape(gx, x.shape)
-        gw = B.matmul(x2.T, a2) if w.requires_grad else None
+        else:
+            if x.requires_grad:
+                gx = B.matmul(a2, w._data.T)
+                if x._data.ndim != 2:
+                    gx = B.reshape(gx, x.shape)
+            gw = B.matmul(x2.T, a2) if w.requires_grad else None
         gb = F.colsum(a2) if (b is not None and b.requires_grad) else None
         return (gx, gw, gb)
 

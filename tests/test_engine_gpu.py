@@ -157,18 +157,33 @@ def test_training_steps_match_oracle_teacher_forced(sk, norm, opt, fuse):
 
 @pytest.mark.parametrize("opt", ["sgd", "adam"])
 def test_free_running_trajectory_layernorm(sk, opt):
-    """30 free-running steps of the LayerNorm model: the loss stays within 1e-4 of the
-    oracle's plus twice the CPU path's own sensitivity (the same oracle with every matmul
-    evaluated in split-K order: an equally valid fp32 result)."""
+    """30 free-running steps of the LayerNorm model against the oracle.
+
+    A free-running trajectory is only defined up to the CPU path's OWN sensitivity: the
+    oracle re-run with its weights perturbed by 1e-7 relative (or with every matmul in
+    split-K order -- an equally valid fp32 result) follows the unperturbed run to ~2e-7
+    for a while and then, at a discrete event (a ReLU mask flipping on one sample), jumps
+    to 1e-3..1e-2 -- with this seed at step 14 for some perturbations, step 24 for others,
+    never for the rest.  The device run is one more such perturbation.  Bars: the first 8
+    steps (before any branch point of the ensemble) within 5e-6; every later step within
+    1e-4 of the oracle plus three times the spread of the CPU ensemble up to that step.
+    The step-exact comparison is the teacher-forced test above."""
     import soket_b200.api as soket
     from soket_b200 import nn
     from soket_b200.optim import SGD, Adam
     dim, hidden, nb, C, B, steps = 784, 100, 3, 10, 100, 30
     om, model, named = make_pair(sk, "layer", dim, hidden, nb, C)
-    om2, _, _ = make_pair(sk, "layer", dim, hidden, nb, C)
     names = om.names()
     mk = (lambda: O.SGD(len(names), lr=0.01)) if opt == "sgd" else (lambda: O.Adam(len(names), lr=0.001, weight_decay=0.001))
-    oo, oo2 = mk(), mk()
+    ens = []
+    for seed in range(8):
+        o2, _, _ = make_pair(sk, "layer", dim, hidden, nb, C)
+        if seed > 0:     # member 0 is unperturbed weights + split-K matmuls
+            r2 = np.random.default_rng(seed)
+            for k in o2.params:
+                o2.params[k] = (o2.params[k] * (1 + 1e-7 * r2.standard_normal(o2.params[k].shape))).astype("float32")
+        ens.append((o2, mk(), seed == 0))
+    oo = mk()
     do = SGD(model.parameters(), lr=0.01) if opt == "sgd" else Adam(model.parameters(), lr=0.001, weight_decay=0.001)
     crit = nn.SoftmaxCrossEntropyLoss()
     rng = np.random.default_rng(2)
@@ -181,13 +196,20 @@ def test_free_running_trajectory_layernorm(sk, opt):
         do.step()
         got.append(loss.item())
         want.append(om.train_step(X, y, oo)[0])
-        with O.matmul_mode("splitk"):
-            pert.append(om2.train_step(X, y, oo2)[0])
+        row = []
+        for o2, opt2, splitk in ens:
+            if splitk:
+                with O.matmul_mode("splitk"):
+                    row.append(o2.train_step(X, y, opt2)[0])
+            else:
+                row.append(o2.train_step(X, y, opt2)[0])
+        pert.append(row)
     got, want, pert = np.array(got), np.array(want), np.array(pert)
-    sens = np.abs(pert - want)
+    spread = np.maximum.accumulate(np.abs(pert - want[:, None]).max(axis=1))
     err = np.abs(got - want)
-    assert np.median(err) <= 2e-5
-    assert err.max() <= 1e-4 * max(1.0, np.abs(want).max()) + 3 * sens.max() + 1e-3, (err.max(), sens.max())
+    assert err[:8].max() <= 5e-6, err[:8]
+    bound = 1e-4 * np.maximum(1.0, np.abs(want)) + 3 * spread + 1e-3
+    assert np.all(err <= bound), (err, spread)
 
 
 def test_module_discovery_quirk_q1(sk):

@@ -235,3 +235,25 @@ def test_f16x3_long_k(sk, M, K, N, dist):
     err = np.abs(got - exact)
     assert err.max() <= 1e-5 * np.abs(exact).max()
     assert np.sqrt((err ** 2).mean()) <= 3e-6 * np.sqrt((exact ** 2).mean())
+
+
+@pytest.mark.parametrize("Bn,I,O", [(512, 384, 256), (1024, 784, 512), (300, 260, 136), (100, 784, 100), (256, 64, 128)])
+@pytest.mark.parametrize("dist", ["uniform", "sample_scales"])
+def test_linear_bwd_shared_split(sk, Bn, I, O, dist):
+    """sk_linear_bwd: dX = adj @ W.T and dW = X.T @ adj from ONE row split of adj; in the dW
+    GEMM adj's per-sample scale is folded into X (exact powers of two).  Per-sample gradient
+    magnitudes spanning 1e-12..1e6 must not cost accuracy.  Small shapes take the two-GEMM
+    fallback inside the same entry point."""
+    rng = np.random.default_rng(Bn + I + O)
+    adj = rng.uniform(-1, 1, (Bn, O))
+    x = rng.uniform(-1, 1, (Bn, I))
+    w = rng.uniform(-1, 1, (I, O))
+    if dist == "sample_scales":
+        adj *= 10.0 ** rng.uniform(-12, 6, (Bn, 1))
+        x *= 10.0 ** rng.uniform(-3, 3, (1, I))
+    adj, x, w = adj.astype("float32"), x.astype("float32"), w.astype("float32")
+    dx, dw = sk.linear_bwd(sk.array(adj), sk.array(x), sk.array(w))
+    dx, dw = sk.asnumpy(dx), sk.asnumpy(dw)
+    assert dx.shape == (Bn, I) and dw.shape == (I, O)
+    assert err_ratio(dx, adj, np.ascontiguousarray(w.T)) <= 2e-6
+    assert err_ratio(dw, np.ascontiguousarray(x.T), adj) <= 2e-6
