@@ -19,7 +19,10 @@ def short(name):
 
 
 def full(rep, out):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
+    if rep.endswith('.csv'):      # already exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > X.csv
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
@@ -44,8 +47,8 @@ def full(rep, out):
         for r in data:
             dur = get(r, 'gpu__time_duration.sum')
             rd, wr = get(r, 'dram__bytes_read.sum'), get(r, 'dram__bytes_write.sum')
-            gbps = (rd + wr) / dur * 1e-3 * 1e6 / 1e3 if dur and rd != '' else ''   # MB/us = TB/s -> GB/s
-            grid = r[col['Grid Size']].strip('()').split(',')[0].strip() if 'Grid Size' in col else ''
+            gbps = (rd + wr) / dur * 1e3 if dur and rd != '' else ''   # MB/us = TB/s -> GB/s
+            grid = 'x'.join(x.strip() for x in r[col['Grid Size']].strip('()').split(',') if x.strip() != '1') or '1' if 'Grid Size' in col else ''
             block = r[col['Block Size']].strip('()').split(',')[0].strip() if 'Block Size' in col else ''
             w.writerow([r[col['ID']], short(r[col['Kernel Name']]), grid, block,
                         get(r, 'launch__registers_per_thread'), get(r, 'launch__shared_mem_per_block_dynamic'),

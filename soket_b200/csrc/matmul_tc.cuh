@@ -131,6 +131,7 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
   const int rows = tiles_m - m_base < group_m ? tiles_m - m_base : group_m;
   tn = within / rows;
   tm = m_base + (within - tn * rows);
+  if (g & 1) tn = tiles_n - 1 - tn;   // serpentine: the next group starts on the B columns still in L2
 }
 
 struct Operand {
