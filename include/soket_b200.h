@@ -265,6 +265,10 @@ int sk_softmax_ce_fwd_bwd(const float *logits, const void *labels, int label_dty
 int sk_add_relu(const float *a, const float *b, float *out, int64_t n);
 /* dropout: out = x * mask * (1/keep), mask ~ Bernoulli(keep) written as fp32 */
 int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float keep);
+/* the same without a stored mask: *seed identifies the Bernoulli draw; sk_dropout_bwd regenerates
+ * the mask from it: out = (adj * r_keep) * mask  (prototypes.pyx:746-760 backward) */
+int sk_dropout_fwd_seeded(const float *x, float *out, int64_t n, float keep, uint64_t *seed);
+int sk_dropout_bwd(const float *adj, float *out, int64_t n, float keep, float r_keep, uint64_t seed);
 /* bias gradient: out[c] = sum_r adj[r, c]  (autodiff.pyx:43-101) ;
  * y_out != NULL applies the relu mask first. */
 int sk_colsum(const float *adj, const float *y_out, float *out, int64_t rows, int64_t cols);

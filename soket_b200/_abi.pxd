@@ -148,6 +148,8 @@ cdef extern from "soket_b200.h" nogil:
                               int64_t rows, int64_t classes)
     int sk_add_relu(const float *a, const float *b, float *out, int64_t n)
     int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float keep)
+    int sk_dropout_fwd_seeded(const float *x, float *out, int64_t n, float keep, uint64_t *seed)
+    int sk_dropout_bwd(const float *adj, float *out, int64_t n, float keep, float r_keep, uint64_t seed)
     int sk_colsum(const float *adj, const float *y_out, float *out, int64_t rows, int64_t cols)
     int sk_accumulate(float *acc, const float *part, int64_t n)
 

@@ -10,7 +10,7 @@ Residual+ReLU (prototypes.pyx:272-273, model.py:34-37), Dropout
 accumulation (autodiff.pyx:30-41), multi-tensor SGD / Adam (optim.pyx:82-269).
 All operands are contiguous float32 device arrays.
 """
-from libc.stdint cimport int64_t
+from libc.stdint cimport int64_t, uint64_t
 from libc.stdlib cimport malloc, free
 
 from soket_b200._abi cimport *
@@ -124,6 +124,21 @@ def dropout(ndarray x, double keep, bint want_mask=True):
     cdef ndarray mask = _new_array(x._ndim, x._shape, SK_F32) if want_mask else None
     _check(sk_dropout_fwd(_fptr(x), _fptr(out), _opt(mask), x._numel(), <float> keep))
     return out, mask
+
+
+def dropout_seeded(ndarray x, double keep):
+    """Dropout forward without a stored mask.  Returns (out, seed); see dropout_bwd."""
+    cdef ndarray out = _new_array(x._ndim, x._shape, SK_F32)
+    cdef uint64_t seed = 0
+    _check(sk_dropout_fwd_seeded(_fptr(x), _fptr(out), x._numel(), <float> keep, &seed))
+    return out, seed
+
+
+def dropout_bwd(ndarray adj, double keep, double r_keep, seed):
+    """(adj * r_keep) * mask with the mask regenerated from the forward's seed."""
+    cdef ndarray out = _new_array(adj._ndim, adj._shape, SK_F32)
+    _check(sk_dropout_bwd(_fptr(adj), _fptr(out), adj._numel(), <float> keep, <float> r_keep, <uint64_t> seed))
+    return out
 
 
 def colsum(ndarray adj, y_out=None):

@@ -969,6 +969,32 @@ dropout_kernel(const float *__restrict__ x, float *__restrict__ out, float *__re
   }
 }
 
+// backward with the mask REGENERATED from the forward's seed (same counter hash): no mask
+// array is stored or read -- 8 B/elem instead of the reference's two passes over three
+// arrays (prototypes.pyx:746-760 backward: adj * (1/keep) * mask).
+__global__ void __launch_bounds__(kNT)
+dropout_bwd_kernel(const float *__restrict__ adj, float *__restrict__ out, int64_t n, float keep,
+                   float r_keep, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * kNT;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * kNT + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ld_stream(reinterpret_cast<const float4 *>(adj) + i);
+    float4 m;
+    m.x = (float)(hash_u32(4 * i + 0, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    m.y = (float)(hash_u32(4 * i + 1, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    m.z = (float)(hash_u32(4 * i + 2, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    m.w = (float)(hash_u32(4 * i + 3, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    float4 o;
+    o.x = (a.x * r_keep) * m.x; o.y = (a.y * r_keep) * m.y; o.z = (a.z * r_keep) * m.z; o.w = (a.w * r_keep) * m.w;
+    st_stream(reinterpret_cast<float4 *>(out) + i, o);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float m = (float)(hash_u32(i, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    out[i] = (adj[i] * r_keep) * m;
+  }
+}
+
 // column sum with optional ReLU mask: out[c] = sum_r (y_out[r,c] > 0 ? adj[r,c] : 0)
 __global__ void __launch_bounds__(kNT)
 colsum_mask_kernel(const float *__restrict__ adj, const float *__restrict__ y_out,
@@ -1157,6 +1183,36 @@ int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float kee
   uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
   ProfScope ps(SK_PROF_EWISE, (double)n * (mask ? 12.0 : 8.0));
   dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, mask, n, keep, r_keep, seed);
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+int sk_dropout_fwd_seeded(const float *x, float *out, int64_t n, float keep, uint64_t *seed_out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(x && out && seed_out, "sk_dropout_fwd_seeded: null pointer");
+  SK_REQUIRE(keep > 0.f && keep <= 1.f, "sk_dropout_fwd_seeded: keep rate must be in (0, 1]");
+  SK_REQUIRE(al16(x) && al16(out), "sk_dropout_fwd_seeded: pointers must be 16-byte aligned");
+  const uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
+  *seed_out = seed;
+  if (n == 0) return SK_OK;
+  const float r_keep = (float)(1.0 / (double)keep);
+  int grid = grid_for((n + 3) / 4, kNT, 8);
+  ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
+  dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, nullptr, n, keep, r_keep, seed);
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+int sk_dropout_bwd(const float *adj, float *out, int64_t n, float keep, float r_keep, uint64_t seed) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(adj && out, "sk_dropout_bwd: null pointer");
+  SK_REQUIRE(al16(adj) && al16(out), "sk_dropout_bwd: pointers must be 16-byte aligned");
+  if (n == 0) return SK_OK;
+  int grid = grid_for((n + 3) / 4, kNT, 8);
+  ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
+  dropout_bwd_kernel<<<grid, kNT, 0, stream()>>>(adj, out, n, keep, r_keep, seed);
   SK_LAUNCH_CHECK();
   return SK_OK;
 }

@@ -1257,10 +1257,13 @@ def add_relu(Tensor a, Tensor b):
 
 class _DropoutOp(Op):
     name = 'dropout'
-    def __init__(self, mask, r_keep):
-        self.mask = mask; self.r_keep = r_keep
-    def bwd(self, node, adj):  # two scalar/elementwise multiplies in the reference
-        return (B.multiply(B.multiply(adj, self.r_keep), self.mask),)
+    def __init__(self, seed, keep, r_keep):
+        self.seed = seed; self.keep = keep; self.r_keep = r_keep
+    def bwd(self, node, adj):  # two scalar/elementwise multiplies in the reference; here one pass,
+        # the mask regenerated from the forward's seed instead of stored
+        if not adj.is_contiguous:
+            adj = B.ascontiguousarray(adj)
+        return (F.dropout_bwd(adj, self.keep, self.r_keep, self.seed),)
 
 
 def dropout(Tensor x, keep_rate):
@@ -1268,8 +1271,8 @@ def dropout(Tensor x, keep_rate):
     if x._dtype.name != 'float32':
         m = B.random.binomial(1, keep_rate, x.shape).astype(x._dtype.name)
         return (x * Tensor._const(m)) * (1.0 / keep_rate)
-    out, mask = F.dropout(B.ascontiguousarray(x._data), keep_rate, True)
-    return Tensor._from_op(_DropoutOp(mask, 1.0 / keep_rate), (x,), out, x._dtype)
+    out, seed = F.dropout_seeded(B.ascontiguousarray(x._data), keep_rate)
+    return Tensor._from_op(_DropoutOp(seed, keep_rate, 1.0 / keep_rate), (x,), out, x._dtype)
 
 
 class _SoftmaxCEOp(Op):

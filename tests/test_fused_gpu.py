@@ -132,6 +132,17 @@ def test_add_relu_colsum_accumulate_dropout(sk, F):
     assert np.array_equal(sk.asnumpy(out), O.dropout_fwd(a, m, 0.75))
     out, mask = F.dropout(sk.array(a), 1.0)
     assert np.array_equal(sk.asnumpy(out), a)
+    # mask-free variant: the backward regenerates the Bernoulli draw from the forward's seed
+    keep = 0.75
+    r_keep = 1.0 / keep
+    out, seed = F.dropout_seeded(sk.array(a), keep)
+    m = (sk.asnumpy(F.dropout_bwd(sk.ones(a.shape, "float32"), keep, 1.0, seed)))      # (1 * 1) * mask
+    assert set(np.unique(m)) <= {0.0, 1.0} and abs(m.mean() - keep) < 0.02
+    assert np.array_equal(sk.asnumpy(out), O.dropout_fwd(a, m, keep))
+    want = np.multiply(np.multiply(b, np.float32(r_keep), dtype="float32"), m, dtype="float32")
+    assert np.array_equal(sk.asnumpy(F.dropout_bwd(sk.array(b), keep, r_keep, seed)), want)
+    out2, seed2 = F.dropout_seeded(sk.array(a), keep)
+    assert seed2 != seed and not np.array_equal(sk.asnumpy(out2), sk.asnumpy(out))        # a fresh draw per call
 
 
 @pytest.mark.parametrize("wd", [0.0, 0.001])
