@@ -45,6 +45,7 @@ DIM, HIDDEN, BLOCKS, CLASSES = 784, 4096, 8, 10
 BATCH_PER_GPU = 8192
 DROP_P = 0.01
 LR = 1e-3
+NORM = "layer"
 
 
 def flops_per_step(batch, hidden=HIDDEN, blocks=BLOCKS, dim=DIM, classes=CLASSES):
@@ -111,14 +112,15 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- model builders
-def build_model(nn, hidden, blocks, drop_p=DROP_P):
+def build_model(nn, hidden, blocks, drop_p=DROP_P, norm="layer"):
     """examples/mlp_resnet/model.py:17-58 out of the given `nn` namespace (the
     reference's soket.nn or soket_b200.nn), keeping `self.fn` so the inner layers are
     visible to parameters() / modules() / train() (quirk Q1)."""
     class ResidualBlock(nn.Sequential):
         def __init__(self, dim, hid):
-            fn = nn.Sequential(nn.Linear(dim, hid), nn.LayerNorm(hid), nn.ReLU(), nn.Dropout(p=drop_p),
-                               nn.Linear(hid, hid), nn.LayerNorm(hid))
+            Norm = nn.LayerNorm if norm == "layer" else nn.BatchNorm1d
+            fn = nn.Sequential(nn.Linear(dim, hid), Norm(hid), nn.ReLU(), nn.Dropout(p=drop_p),
+                               nn.Linear(hid, hid), Norm(hid))
             super().__init__(nn.Residual(fn), nn.ReLU())
             self.fn = fn
 
@@ -170,7 +172,7 @@ def cpu_reference_step_time(batch, steps, warmup, hidden=HIDDEN, blocks=BLOCKS):
         from soket.nn.init import kaiming_normal
         from soket.optim import Adam
         np.random.seed(0)
-        model = build_model(rnn, hidden, blocks)
+        model = build_model(rnn, hidden, blocks, norm=NORM)
         for m in model.modules():
             if type(m).__name__ == "Linear":
                 kaiming_normal(m.weight)
@@ -223,7 +225,8 @@ def run_reference(args, env):
 
 def workload_config(args, world):
     return {
-        "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, LayerNorm, "
+        "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, "
+                    f"{'LayerNorm' if args.norm == 'layer' else 'BatchNorm1d'}, "
                     f"dropout={DROP_P}) train step, Adam lr=1e-3, fp32, all {4 + 8 * args.blocks} tensors trainable "
                     f"(BASELINE.json configs[3]; configs[4] for N>1)",
         "batch_per_gpu": args.batch, "global_batch": args.batch * world,
@@ -244,7 +247,7 @@ def run_ours(args, env):
     rdv = dp.Rendezvous(env) if env.world > 1 else None
 
     sk.random.seed(1234)          # identical initial weights on every rank
-    model = build_model(nn, args.hidden, args.blocks)
+    model = build_model(nn, args.hidden, args.blocks, norm=args.norm)
     for m in model.modules():
         if type(m).__name__ == "Linear":
             nn.kaiming_normal(m.weight)
@@ -431,9 +434,13 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS)
     ap.add_argument("--cpu-sample-batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--norm", default="layer", choices=["layer", "batch"],
+                    help="normalisation of the residual blocks (the bench line is LayerNorm, as examples/mlp_resnet/model.py)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    global NORM
+    NORM = args.norm
     from soket_b200 import dp
     env = dp.read_env()
     if args.impl == "reference":
