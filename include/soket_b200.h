@@ -116,8 +116,20 @@ int sk_prof_enable(int on);
 int sk_prof_reset(void);
 int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *total_work);
 
-/* CUDA-graph capture of a static-shape step */
+/* CUDA-graph capture of a static-shape step.
+ * Allocation arenas: between sk_arena_begin(id) and sk_arena_end() every sk_malloc is served
+ * from (and every block returns to) arena `id`, so the buffers a graph was captured with stay
+ * reserved for its replays.  During a capture a miss in the arena is an error (no cudaMalloc
+ * inside a capture): run the step once or twice inside the arena first.
+ * sk_rng_epoch_advance(): bumps the device-side counter the dropout kernels mix into their
+ * seeds at run time -- captured as the first node, it gives every replay fresh masks. */
+int sk_arena_create(int *arena);
+int sk_arena_begin(int arena);
+int sk_arena_end(void);
+int sk_arena_destroy(int arena);
+int sk_rng_epoch_advance(void);
 int sk_graph_begin(void);
+int sk_graph_capturing(void);   /* 1 between sk_graph_begin and sk_graph_end */
 int sk_graph_end(void **graph_exec);
 int sk_graph_launch(void *graph_exec);
 int sk_graph_destroy(void *graph_exec);

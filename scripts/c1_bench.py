@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=600)
 ap.add_argument("--warmup", type=int, default=20)
 ap.add_argument("--variant", default="fn", choices=["fn", "verbatim"])
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--graph", action="store_true", help="also time the step as one CUDA-graph launch (soket_b200.graph.StaticStep)")
 args = ap.parse_args()
 DIM, HID, NB, C, B = 784, 100, 3, 10, 100
 rng = np.random.default_rng(0)
@@ -67,6 +68,43 @@ n0 = sk.launch_count()
 sec, loss = run(gnn, soket.Tensor, GSGD, gnn.kaiming_normal, sk.synchronize, lambda a: soket.Tensor(a))
 launches = (sk.launch_count() - n0) / (args.steps + args.warmup)
 out["gpu"] = {"ms_per_step": sec * 1e3, "samples_per_s": B / sec, "launches_per_step": launches, "last_loss": loss}
+if args.graph:
+    from soket_b200.graph import StaticStep
+    np.random.seed(0)
+    model = ref_model.build_model(gnn, DIM, HID, NB, C, norm="layer", drop_prob=0.01, retain_fn=args.variant == "fn")
+    for m in model.modules():
+        if type(m).__name__ == "Linear":
+            gnn.kaiming_normal(m.weight)
+    opt = GSGD(model.parameters(), lr=0.01)
+    crit = gnn.SoftmaxCrossEntropyLoss()
+    model.train(True)
+    dev_batches = [(sk.array(X[i * B:(i + 1) * B]), sk.array(y[i * B:(i + 1) * B])) for i in range(64)]
+    xb, yb = soket.Tensor(X[:B]), soket.Tensor(y[:B])
+
+    def gstep():
+        loss = crit(model(xb), yb)
+        loss.backward()
+        opt.step()
+        return loss
+    g = StaticStep(gstep)
+
+    def run_graph(i):
+        bx, by = dev_batches[i % 64]
+        xb._data[:] = bx               # device-side copy of the batch into the static input buffers
+        yb._data[:] = by
+        g.launch()
+        return g.loss.item()           # loss.item() every step, as examples/mlp_resnet/model.py:89
+    for i in range(args.warmup):
+        run_graph(i)
+    sk.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = run_graph(i)
+    sk.synchronize()
+    sec_g = (time.perf_counter() - t0) / args.steps
+    out["gpu_graph"] = {"ms_per_step": sec_g * 1e3, "samples_per_s": B / sec_g, "last_loss": last,
+                        "launches_per_step": "1 graph + 2 batch copies"}
+    g.close()
 if not args.no_cpu:
     ref = ref_model.import_reference()
     if ref is not None:

@@ -98,7 +98,13 @@ cdef extern from "soket_b200.h" nogil:
     int sk_prof_reset()
     int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *total_work)
 
+    int sk_arena_create(int *arena)
+    int sk_arena_begin(int arena)
+    int sk_arena_end()
+    int sk_arena_destroy(int arena)
+    int sk_rng_epoch_advance()
     int sk_graph_begin()
+    int sk_graph_capturing()
     int sk_graph_end(void **graph_exec)
     int sk_graph_launch(void *graph_exec)
     int sk_graph_destroy(void *graph_exec)

@@ -1478,6 +1478,34 @@ cdef class Event:
         return ms
 
 
+def arena_create():
+    """A private allocation arena (see sk_arena_* in include/soket_b200.h)."""
+    cdef int a = 0
+    _check(sk_arena_create(&a))
+    return a
+
+
+def arena_begin(int arena):
+    _check(sk_arena_begin(arena))
+
+
+def arena_end():
+    _check(sk_arena_end())
+
+
+def arena_destroy(int arena):
+    _check(sk_arena_destroy(arena))
+
+
+def is_capturing():
+    return sk_graph_capturing() != 0
+
+
+def rng_epoch_advance():
+    """Bump the device-side counter mixed into dropout seeds (first node of a captured step)."""
+    _check(sk_rng_epoch_advance())
+
+
 cdef class Graph:
     """Captured CUDA graph of a static-shape step (SURVEY.md section 8f-1)."""
     cdef void *_exec

@@ -50,6 +50,8 @@ Context &ctx();
 int ensure_init();
 void note_launch();
 inline cudaStream_t stream() { return ctx().stream; }
+// device-resident counter mixed into dropout seeds at RUN time; a captured graph advances it per replay
+const uint64_t *rng_epoch_ptr();
 
 // ---- per-family profiling (sk_prof_*) -------------------------------------------
 // Usage inside a launcher:  ProfScope ps(SK_PROF_GEMM_TC, flops);  ... launch ...

@@ -946,7 +946,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t idx, uint64_t seed) {
 }
 __global__ void __launch_bounds__(kNT)
 dropout_kernel(const float *__restrict__ x, float *__restrict__ out, float *__restrict__ mask,
-               int64_t n, float keep, float r_keep, uint64_t seed) {
+               int64_t n, float keep, float r_keep, uint64_t seed, const uint64_t *__restrict__ epoch) {
+  seed += *epoch * 0xD1B54A32D192ED03ull;   // replay counter of a captured graph (0 in eager mode)
   const int64_t stride = (int64_t)gridDim.x * kNT;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * kNT + threadIdx.x; i < n4; i += stride) {
@@ -974,7 +975,8 @@ dropout_kernel(const float *__restrict__ x, float *__restrict__ out, float *__re
 // arrays (prototypes.pyx:746-760 backward: adj * (1/keep) * mask).
 __global__ void __launch_bounds__(kNT)
 dropout_bwd_kernel(const float *__restrict__ adj, float *__restrict__ out, int64_t n, float keep,
-                   float r_keep, uint64_t seed) {
+                   float r_keep, uint64_t seed, const uint64_t *__restrict__ epoch) {
+  seed += *epoch * 0xD1B54A32D192ED03ull;
   const int64_t stride = (int64_t)gridDim.x * kNT;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * kNT + threadIdx.x; i < n4; i += stride) {
@@ -1182,7 +1184,7 @@ int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float kee
   int grid = grid_for((n + 3) / 4, kNT, 8);
   uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
   ProfScope ps(SK_PROF_EWISE, (double)n * (mask ? 12.0 : 8.0));
-  dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, mask, n, keep, r_keep, seed);
+  dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, mask, n, keep, r_keep, seed, rng_epoch_ptr());
   SK_LAUNCH_CHECK();
   return SK_OK;
 }
@@ -1199,7 +1201,7 @@ int sk_dropout_fwd_seeded(const float *x, float *out, int64_t n, float keep, uin
   const float r_keep = (float)(1.0 / (double)keep);
   int grid = grid_for((n + 3) / 4, kNT, 8);
   ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
-  dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, nullptr, n, keep, r_keep, seed);
+  dropout_kernel<<<grid, kNT, 0, stream()>>>(x, out, nullptr, n, keep, r_keep, seed, rng_epoch_ptr());
   SK_LAUNCH_CHECK();
   return SK_OK;
 }
@@ -1212,7 +1214,7 @@ int sk_dropout_bwd(const float *adj, float *out, int64_t n, float keep, float r_
   if (n == 0) return SK_OK;
   int grid = grid_for((n + 3) / 4, kNT, 8);
   ProfScope ps(SK_PROF_EWISE, (double)n * 8.0);
-  dropout_bwd_kernel<<<grid, kNT, 0, stream()>>>(adj, out, n, keep, r_keep, seed);
+  dropout_bwd_kernel<<<grid, kNT, 0, stream()>>>(adj, out, n, keep, r_keep, seed, rng_epoch_ptr());
   SK_LAUNCH_CHECK();
   return SK_OK;
 }

@@ -42,10 +42,17 @@ Context &ctx() {
 // One compute stream => a freed block may be handed out again immediately
 // (stream order protects it).  Blocks are cached by rounded size; nothing is
 // returned to the driver until sk_empty_cache() or an OOM retry.
+// Arenas: arena 0 is the process-wide cache.  A CUDA-graph capture allocates from a
+// private arena (sk_arena_*): the blocks its kernels were captured with stay reserved
+// for the graph -- they return to the arena's own free lists, which nobody else draws
+// from -- so replays never collide with later eager allocations.
+static bool g_capturing = false;
 struct Allocator {
-  std::map<size_t, std::vector<void *>> free_blocks;
-  std::unordered_map<void *, size_t> live;
+  struct Block { size_t size; int arena; };
+  std::map<int, std::map<size_t, std::vector<void *>>> free_blocks;   // arena -> size -> blocks
+  std::unordered_map<void *, Block> live;
   size_t in_use = 0, reserved = 0, peak = 0;
+  int cur_arena = 0, next_arena = 1;
 
   static size_t round_size(size_t n) {
     if (n == 0) n = 1;
@@ -54,11 +61,17 @@ struct Allocator {
   }
   int alloc(size_t nbytes, void **out) {
     size_t sz = round_size(nbytes);
-    auto it = free_blocks.find(sz);
-    if (it != free_blocks.end() && !it->second.empty()) {
+    auto &fl = free_blocks[cur_arena];
+    auto it = fl.find(sz);
+    if (it != fl.end() && !it->second.empty()) {
       *out = it->second.back();
       it->second.pop_back();
     } else {
+      if (g_capturing) {
+        set_error("sk_malloc: %zu bytes not available in the capture arena -- the allocation pattern of the "
+                  "captured step differs from its dry runs", sz);
+        return SK_ERR_UNSUPPORTED;
+      }
       cudaError_t e = cudaMalloc(out, sz);
       if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
@@ -68,7 +81,7 @@ struct Allocator {
       if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
       reserved += sz;
     }
-    live[*out] = sz;
+    live[*out] = Block{sz, cur_arena};
     in_use += sz;
     if (in_use > peak) peak = in_use;
     return SK_OK;
@@ -79,22 +92,27 @@ struct Allocator {
       set_error("sk_free: pointer %p was not allocated by sk_malloc", p);
       return SK_ERR_ARG;
     }
-    size_t sz = it->second;
+    const Block b = it->second;
     live.erase(it);
-    in_use -= sz;
-    free_blocks[sz].push_back(p);
+    in_use -= b.size;
+    free_blocks[b.arena][b.size].push_back(p);
     return SK_OK;
   }
-  void release_cached() {
-    cudaStreamSynchronize(ctx().stream);
-    for (auto &kv : free_blocks) {
+  void release_arena_cached(int arena) {
+    auto ia = free_blocks.find(arena);
+    if (ia == free_blocks.end()) return;
+    for (auto &kv : ia->second) {
       for (void *p : kv.second) {
         cudaFree(p);
         reserved -= kv.first;
       }
-      kv.second.clear();
     }
-    free_blocks.clear();
+    free_blocks.erase(ia);
+  }
+  // arena 0 only: graph arenas keep their blocks until sk_arena_destroy
+  void release_cached() {
+    cudaStreamSynchronize(ctx().stream);
+    release_arena_cached(0);
   }
 };
 static Allocator &allocator() {
@@ -135,6 +153,10 @@ void prof_end(int family, double work) {
   cudaEventRecord(e, ctx().stream);
   g_prof[family].push_back({g_prof_open[family], e, work});
 }
+
+static uint64_t *g_epoch_dev = nullptr;
+const uint64_t *rng_epoch_ptr() { return g_epoch_dev; }
+__global__ void epoch_advance_kernel(uint64_t *e) { *e += 1; }
 
 static void *g_flush_buf = nullptr;
 static size_t g_flush_bytes = 0;
@@ -187,6 +209,8 @@ int sk_init(int device) {
   c.l2_bytes = (size_t)prop.l2CacheSize;
   SK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   SK_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  SK_CUDA(cudaMalloc((void **)&g_epoch_dev, sizeof(uint64_t)));
+  SK_CUDA(cudaMemset(g_epoch_dev, 0, sizeof(uint64_t)));
   c.device = device;
   c.ready = true;
   return SK_OK;
@@ -222,6 +246,39 @@ int sk_free(void *ptr) {
 int sk_empty_cache(void) {
   if (!ctx().ready) return SK_OK;
   allocator().release_cached();
+  return SK_OK;
+}
+
+int sk_arena_create(int *arena) {
+  SK_REQUIRE(arena != nullptr, "sk_arena_create: null out pointer");
+  *arena = allocator().next_arena++;
+  return SK_OK;
+}
+int sk_arena_begin(int arena) {
+  SK_REQUIRE(arena > 0 && arena < allocator().next_arena, "sk_arena_begin: unknown arena %d", arena);
+  SK_REQUIRE(allocator().cur_arena == 0, "sk_arena_begin: arena %d is already active", allocator().cur_arena);
+  allocator().cur_arena = arena;
+  return SK_OK;
+}
+int sk_arena_end(void) {
+  allocator().cur_arena = 0;
+  return SK_OK;
+}
+int sk_arena_destroy(int arena) {
+  SK_REQUIRE(arena > 0, "sk_arena_destroy: arena 0 is the process cache (use sk_empty_cache)");
+  Allocator &a = allocator();
+  SK_REQUIRE(a.cur_arena != arena, "sk_arena_destroy: arena %d is active", arena);
+  if (ctx().ready) SK_CUDA(cudaStreamSynchronize(ctx().stream));
+  a.release_arena_cached(arena);
+  for (auto &kv : a.live)       // blocks still held by the caller fall back to the process cache when freed
+    if (kv.second.arena == arena) kv.second.arena = 0;
+  return SK_OK;
+}
+int sk_rng_epoch_advance(void) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  epoch_advance_kernel<<<1, 1, 0, ctx().stream>>>(g_epoch_dev);
+  SK_LAUNCH_CHECK();
   return SK_OK;
 }
 
@@ -363,12 +420,16 @@ int sk_prof_collect(int family, int64_t *launches, double *total_ms, double *tot
 int sk_graph_begin(void) {
   int rc = ensure_init();
   if (rc) return rc;
-  SK_CUDA(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+  SK_REQUIRE(!g_capturing, "sk_graph_begin: a capture is already in progress");
+  SK_CUDA(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeRelaxed));
+  g_capturing = true;   // sk_malloc may only be served from the active arena's free lists now
   return SK_OK;
 }
+int sk_graph_capturing(void) { return g_capturing ? 1 : 0; }
 int sk_graph_end(void **graph_exec) {
   SK_REQUIRE(graph_exec != nullptr, "null out pointer");
   cudaGraph_t g = nullptr;
+  g_capturing = false;
   SK_CUDA(cudaStreamEndCapture(ctx().stream, &g));
   cudaGraphExec_t ge = nullptr;
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);

@@ -99,6 +99,9 @@ cdef class Adam(Optimizer):
         self._v = [None] * len(self._params)
 
     def step(self):
+        if B.is_capturing():
+            raise RuntimeError("Adam.step inside a CUDA-graph capture: the bias corrections 1 - beta^t are host "
+                               "scalars (optim.pyx:191-195) and would be frozen in the graph; capture SGD steps only")
         ps, gs, idx = self._live()
         # first-step parameters (no state yet) and the rest go to separate launches:
         # optim.pyx:224-238 initialises m, v without the beta * 0 term
