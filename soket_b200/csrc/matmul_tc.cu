@@ -411,6 +411,7 @@ static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &o
   p.epilogue = g.epilogue;
   p.row_inv = nullptr; p.col_inv = nullptr;
   p.group_m = 1;
+  p.sched = nullptr;
   p.tiles_m = (int)((g.M + BM - 1) / BM);
   p.tiles_n = (int)((g.N + BN - 1) / BN);
   const int tiles = p.tiles_m * p.tiles_n;

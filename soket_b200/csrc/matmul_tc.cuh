@@ -118,6 +118,7 @@ struct TcParams {
   int group_m;            // M-tiles per rasterisation group (tile_coords)
   const float *row_inv;   // fp16x3: 2^-e per output row / column (operand scales to undo)
   const float *col_inv;
+  int *sched;             // CTA-pair kernel: {next tile, finished pairs} for dynamic tile scheduling (NULL = static)
 };
 
 // Tile rasterisation: groups of `group_m` M-tiles are swept across all N-tiles (M fastest

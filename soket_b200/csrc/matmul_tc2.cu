@@ -16,6 +16,14 @@
 //   tfull[a]  (own copy, count 1): multicast commit -> each CTA's epilogue
 //   tempty[a] (leader's copy, count 2 x epilogue warps): every epilogue warp of both
 //             CTAs arrives (the peer's remotely)
+//
+// Tile scheduling is DYNAMIC: a scheduler warp in the leader CTA hands out tile indices
+// from a global counter (the first tile of each pair is static) through a 2-deep ring that
+// exists in both CTAs (sfull[i] per CTA; sempty[i] on the leader, count = every reader of
+// both CTAs).  A pair whose SMs were busy when the kernel started -- an NCCL all-reduce of
+// the previous layer's gradients running on the comm stream -- simply claims fewer tiles,
+// where the static `tile += pairs` order made the whole GEMM wait for its slowest pair
+// (measured: +3.5 ms of GEMM time per step at 8 GPUs).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -74,10 +82,33 @@ __device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t desc_a, uin
   }
 }
 
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// wait with cluster-scope acquire: the value published next to the barrier came from the other CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 constexpr int BM2 = 256;          // rows per CTA pair
 constexpr int BMH = 128;          // rows per CTA
 constexpr int BN2 = 256;          // columns per pair tile; each CTA stages BN2/2 of B
-constexpr int kTc2Threads = 64 + 128 * (BN2 / 128);
+constexpr int kTc2Threads = 64 + 128 * (BN2 / 128) + 32;   // TMA, MMA, 8 epilogue warps, scheduler
+constexpr int SD = 2;             // tile-ring depth: tiles a pair may claim ahead
 
 template <int KIND, int STAGES, int CHUNK_KB, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1)
@@ -113,13 +144,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t *empty_bar = bars + STAGES;
   uint64_t *tfull_bar = bars + 2 * STAGES;
   uint64_t *tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+  uint64_t *sfull_bar = bars + 2 * STAGES + 4;      // [SD] tile id published (own copy)
+  uint64_t *sempty_bar = bars + 2 * STAGES + 4 + SD;  // [SD] tile id read by everyone (leader's copy)
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4 + 2 * SD);
+  volatile int *tile_ring = (volatile int *)(tmem_slot + 2);   // [SD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_tiles = p.tiles_m * p.tiles_n;      // tiles of 256 x 256
   const int num_kb = (p.K + BK - 1) / BK;
+  const bool dyn = p.sched != nullptr;
+  // every reader of a ring slot: TMA thread + epilogue warps of both CTAs + the MMA thread
+  constexpr int kRingReaders = 2 * (1 + EPI_WARPS) + 1;
+
+  // The it-th tile of this pair, or -1.  Called by one lane (TMA / MMA threads) or by a whole
+  // warp (`warp_wide`, epilogue); `elected` (one lane per caller) releases the ring slot once
+  // every calling lane has the value.
+  int sched_it = 0;
+  auto next_tile = [&](bool elected, bool warp_wide) -> int {
+    int t;
+    if (!dyn) {
+      t = pair + sched_it * num_pairs;
+      if (t >= num_tiles) t = -1;
+    } else {
+      const int sl = sched_it % SD;
+      mbar_wait_cluster(smem_u32(&sfull_bar[sl]), (uint32_t)((sched_it / SD) & 1));
+      t = tile_ring[sl];
+      if (warp_wide) __syncwarp();
+      if (elected && t >= -1) {   // the (always true) test makes the arrive depend on the loaded value
+        if (rank == 0) mbar_arrive(smem_u32(&sempty_bar[sl]));
+        else mbar_arrive_cluster_relaxed(map_to_cta(smem_u32(&sempty_bar[sl]), 0));
+      }
+    }
+    ++sched_it;
+    return t;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -132,6 +192,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
       mbar_init(smem_u32(&tempty_bar[a]), 2 * EPI_WARPS);
+    }
+    for (int i = 0; i < SD; ++i) {
+      mbar_init(smem_u32(&sfull_bar[i]), 1);
+      mbar_init(smem_u32(&sempty_bar[i]), kRingReaders);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -149,7 +213,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int tile = next_tile(true, false); tile >= 0; tile = next_tile(true, false)) {
         int tm, tn;
         tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
         const int m0 = tm * BM2 + (int)rank * BMH;       // this CTA's A rows
@@ -195,7 +259,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int tile = next_tile(true, false); tile >= 0; tile = next_tile(true, false)) {
         for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB) {
           const int kb1 = kb0 + CHUNK_KB < num_kb ? kb0 + CHUNK_KB : num_kb;
           mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);   // both CTAs drained this buffer
@@ -225,6 +289,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
     }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ===================== tile scheduler (leader CTA only) =====================
+    if (dyn && rank == 0 && lane == 0) {
+      for (int it = 0;; ++it) {
+        const int sl = it % SD;
+        mbar_wait_cluster(smem_u32(&sempty_bar[sl]), (uint32_t)(((it / SD) & 1) ^ 1));   // all 19 readers done
+        int t = it == 0 ? pair : num_pairs + atomicAdd(p.sched, 1);
+        if (t >= num_tiles) t = -1;
+        tile_ring[sl] = t;
+        st_cluster_u32(map_to_cta(smem_u32((const void *)&tile_ring[sl]), 1), (uint32_t)t);
+        mbar_arrive(smem_u32(&sfull_bar[sl]));
+        mbar_arrive_cluster_release(map_to_cta(smem_u32(&sfull_bar[sl]), 1));
+        if (t < 0) break;
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
     const int q = warp & 3;
@@ -232,7 +311,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 4 == 0) && ((((uintptr_t)p.c) & 15) == 0);
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int tile = next_tile(lane == 0, true); tile >= 0; tile = next_tile(lane == 0, true)) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
       const int m0 = tm * BM2 + (int)rank * BMH;
@@ -305,6 +384,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   // neither CTA may exit (or free TMEM) while its partner can still touch its smem / TMEM
   tc_fence_before();
   cluster_sync_all();
+  if (dyn && rank == 0 && threadIdx.x == 0) {
+    // the last pair to finish re-arms the counters for the next launch on this stream
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == num_pairs - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -344,6 +432,13 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   p.tiles_n = (int)((g.N + BN2 - 1) / BN2);
   static const int group_env = getenv("SOKET_B200_GEMM_GROUP_M") ? atoi(getenv("SOKET_B200_GEMM_GROUP_M")) : 8;
   p.group_m = group_env < 1 ? 1 : group_env;
+  static const int dyn_env = getenv("SOKET_B200_GEMM_DYNAMIC") ? atoi(getenv("SOKET_B200_GEMM_DYNAMIC")) : 1;
+  static int *sched_dev = nullptr;
+  if (dyn_env && !sched_dev) {
+    SK_CUDA(cudaMalloc((void **)&sched_dev, 2 * sizeof(int)));
+    SK_CUDA(cudaMemsetAsync(sched_dev, 0, 2 * sizeof(int), stream()));
+  }
+  p.sched = dyn_env ? sched_dev : nullptr;
   const int tiles = p.tiles_m * p.tiles_n;
   const int max_pairs = ctx().num_sms / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
