@@ -274,26 +274,39 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
                      const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
                      const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
                      float *__restrict__ dresidual, float *__restrict__ part_g,
-                     float *__restrict__ part_b, int64_t R, int C, int stages) {
+                     float *__restrict__ part_b, int64_t R, int C, int stages, int *__restrict__ sched) {
   extern __shared__ __align__(128) uint8_t ln_sm[];
   float *red = reinterpret_cast<float *>(ln_sm);
   uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
+  volatile int *row_ring = reinterpret_cast<volatile int *>(ln_sm + 224);   // [kLnMaxStages] claimed rows
   float *data = reinterpret_cast<float *>(ln_sm + kLnHeader);
   const int nbuf = mask_mode == 2 ? 3 : 2;
   const uint32_t row_bytes = (uint32_t)C * 4u;
   const int t = threadIdx.x;
   const int C4 = C >> 2;
   const float inv_n = 1.0f / (float)C;
-  const int64_t n_it = (R - blockIdx.x + gridDim.x - 1) / gridDim.x;   // rows of this block
 
-  auto issue = [&](int64_t it) {   // thread 0 only
+  // Rows are CLAIMED from a global counter as their loads are issued (the first one is
+  // static): a block that starts late -- its SM was running the overlapped NCCL all-reduce --
+  // takes fewer rows instead of stretching the kernel (static striding cost +0.8 ms per step
+  // under data parallelism).  The claimed row travels to the consumers in `row_ring`, published
+  // by the same mbarrier phase that says its bytes have landed; -1 ends the walk.
+  int64_t claimed = 0;   // thread 0: rows claimed so far
+  auto issue = [&](int64_t it) {   // thread 0 only; `it` counts this block's claims
     const int sl = (int)(it % stages);
-    const int64_t row = blockIdx.x + it * gridDim.x;
+    int64_t row = it == 0 ? (int64_t)blockIdx.x : (int64_t)gridDim.x + atomicAdd(sched, 1);
+    if (row >= R) {
+      row_ring[sl] = -1;
+      ln_mbar_expect(&full[sl], 0);   // plain arrive: the phase completes with no bytes
+      return false;
+    }
+    row_ring[sl] = (int)row;
     float *dst = data + (size_t)sl * nbuf * C;
     ln_mbar_expect(&full[sl], row_bytes * nbuf);
     ln_bulk_load(dst, adj + row * C, row_bytes, &full[sl]);
     ln_bulk_load(dst + C, x + row * C, row_bytes, &full[sl]);
     if (nbuf == 3) ln_bulk_load(dst + 2 * C, y_out + row * C, row_bytes, &full[sl]);
+    return true;
   };
   if (t == 0) {
     for (int i = 0; i < stages; ++i) ln_mbar_init(&full[i], 1);
@@ -301,21 +314,23 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  bool more = true;      // thread 0: the counter has not run out yet
   if (t == 0)
-    for (int64_t it = 0; it < stages - 1 && it < n_it; ++it) issue(it);
+    for (; claimed < stages - 1 && more; ++claimed) more = issue(claimed);
 
   float4 ag[VPT], ab[VPT];
 #pragma unroll
   for (int j = 0; j < VPT; ++j) { ag[j] = make_float4(0.f, 0.f, 0.f, 0.f); ab[j] = ag[j]; }
 
-  for (int64_t it = 0; it < n_it; ++it) {
-    // the slot refilled here was read in iteration it-1, before that iteration's block syncs
-    if (t == 0 && it + stages - 1 < n_it) issue(it + stages - 1);
+  for (int64_t it = 0;; ++it) {
+    // the slot refilled here was read in iteration it-1, before that iteration's block sync
+    if (t == 0 && more) { more = issue(claimed); ++claimed; }
     const int sl = (int)(it % stages);
-    const int64_t row = blockIdx.x + it * gridDim.x;
+    ln_mbar_wait(&full[sl], (uint32_t)((it / stages) & 1));
+    const int64_t row = row_ring[sl];
+    if (row < 0) break;
     const float mean = mean_in[row];
     const float r = rstd_in[row];
-    ln_mbar_wait(&full[sl], (uint32_t)((it / stages) & 1));
     const float4 *ar = reinterpret_cast<const float4 *>(data + (size_t)sl * nbuf * C);
     const float4 *xr = ar + C4;
     const float4 *yr = ar + 2 * C4;
@@ -385,6 +400,14 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
         reinterpret_cast<float4 *>(part_g + prow * C)[i] = ag[j];
         reinterpret_cast<float4 *>(part_b + prow * C)[i] = ab[j];
       }
+    }
+  }
+  if (t == 0) {   // the last block to finish re-arms the row counter for the next launch
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
     }
   }
 }
@@ -596,8 +619,13 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
         SK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kLnHeader));
         attr_set = true;
       }
+      static int *sched_dev = nullptr;
+      if (!sched_dev) {
+        SK_CUDA(cudaMalloc((void **)&sched_dev, 2 * sizeof(int)));
+        SK_CUDA(cudaMemsetAsync(sched_dev, 0, 2 * sizeof(int), stream()));
+      }
       kern<<<grid, kNT, smem, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, part,
-                                          part ? part + P * C : nullptr, R, C, stages);
+                                          part ? part + P * C : nullptr, R, C, stages, sched_dev);
     } else {
       ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
                                                          dresidual, part, part ? part + P * C : nullptr, R, C);
