@@ -85,6 +85,11 @@ int sk_d2d(void *dst, const void *src, size_t nbytes);
 int sk_memset(void *dst, int byte, size_t nbytes);
 
 /* timing + launch accounting (bench.py: CUDA events on the launching stream) */
+/* host -> device input prefetch on a dedicated copy stream: ordered after the compute work
+ * queued so far, overlapping the work queued next; sk_prefetch_wait() joins it back into the
+ * compute stream (Tensor(host_array) of the reference, tensor.pyx:386-442, made asynchronous) */
+int sk_h2d_prefetch(void *dst, const void *src, size_t nbytes);
+int sk_prefetch_wait(void);
 int sk_event_create(void **ev);
 int sk_event_record(void *ev);
 int sk_event_sync(void *ev);

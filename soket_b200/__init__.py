@@ -41,7 +41,7 @@ from ._core import (  # noqa: F401,E402
     MM_AUTO, MM_SIMT, MM_TF32X3, MM_TF32, MM_BF16, MM_F16X3,
     random, device_count, is_available, init, synchronize, launch_count, flush_l2,
     memory_stats, empty_cache, version, Event, Graph, PinnedBuffer,
-    arena_create, arena_begin, arena_end, arena_destroy, rng_epoch_advance, is_capturing,
+    arena_create, arena_begin, arena_end, arena_destroy, rng_epoch_advance, is_capturing, prefetch_wait,
     profile_enable, profile_reset, profile_collect,
 )
 

@@ -86,6 +86,8 @@ cdef extern from "soket_b200.h" nogil:
     int sk_d2d(void *dst, const void *src, size_t nbytes)
     int sk_memset(void *dst, int byte, size_t nbytes)
 
+    int sk_h2d_prefetch(void *dst, const void *src, size_t nbytes)
+    int sk_prefetch_wait()
     int sk_event_create(void **ev)
     int sk_event_record(void *ev)
     int sk_event_sync(void *ev)

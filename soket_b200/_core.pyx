@@ -1497,6 +1497,11 @@ def arena_destroy(int arena):
     _check(sk_arena_destroy(arena))
 
 
+def prefetch_wait():
+    """The compute stream waits for the most recent PinnedBuffer.prefetch_to_device."""
+    _check(sk_prefetch_wait())
+
+
 def is_capturing():
     return sk_graph_capturing() != 0
 
@@ -1568,6 +1573,13 @@ cdef class PinnedBuffer:
         if not dst._is_contiguous() or <size_t> dst.nbytes != self._nbytes:
             raise ValueError('PinnedBuffer.copy_to_device: size / layout mismatch')
         _check(sk_h2d_async(<void *> dst._ptr, self._p, self._nbytes))
+
+    def prefetch_to_device(self, ndarray dst):
+        """Async H2D on the copy stream: after the compute work queued so far, overlapping what
+        is queued next; call `prefetch_wait()` before the first kernel that reads `dst`."""
+        if not dst._is_contiguous() or <size_t> dst.nbytes != self._nbytes:
+            raise ValueError('PinnedBuffer.prefetch_to_device: size / layout mismatch')
+        _check(sk_h2d_prefetch(<void *> dst._ptr, self._p, self._nbytes))
 
     def copy_from_device(self, ndarray src):
         """Async D2H on the compute stream (synchronize before reading)."""

@@ -45,6 +45,7 @@ struct Context {
   size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host -> device input prefetch (sk_h2d_prefetch)
 };
 Context &ctx();
 int ensure_init();

@@ -209,6 +209,7 @@ int sk_init(int device) {
   c.l2_bytes = (size_t)prop.l2CacheSize;
   SK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   SK_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  SK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   SK_CUDA(cudaMalloc((void **)&g_epoch_dev, sizeof(uint64_t)));
   SK_CUDA(cudaMemset(g_epoch_dev, 0, sizeof(uint64_t)));
   c.device = device;
@@ -228,6 +229,7 @@ int sk_sync(void) {
   if (!ctx().ready) return SK_OK;
   SK_CUDA(cudaStreamSynchronize(ctx().stream));
   SK_CUDA(cudaStreamSynchronize(ctx().comm_stream));
+  SK_CUDA(cudaStreamSynchronize(ctx().copy_stream));
   return SK_OK;
 }
 
@@ -332,6 +334,31 @@ int sk_d2h_async(void *dst, const void *src, size_t nbytes) {
   SK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
   return SK_OK;
 }
+// Input prefetch: the copy runs on a dedicated stream, ordered AFTER everything already queued
+// on the compute stream (so a staging buffer the previous step read is safe to overwrite) and
+// concurrently with whatever is queued next; sk_prefetch_wait() makes the compute stream wait
+// for the most recent prefetch.  With two staging buffers the batch of step k+1 crosses PCIe
+// while step k computes.
+static cudaEvent_t g_ev_pf_compute = nullptr, g_ev_pf_done = nullptr;
+int sk_h2d_prefetch(void *dst, const void *src, size_t nbytes) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!g_ev_pf_compute) {
+    SK_CUDA(cudaEventCreateWithFlags(&g_ev_pf_compute, cudaEventDisableTiming));
+    SK_CUDA(cudaEventCreateWithFlags(&g_ev_pf_done, cudaEventDisableTiming));
+  }
+  SK_CUDA(cudaEventRecord(g_ev_pf_compute, ctx().stream));
+  SK_CUDA(cudaStreamWaitEvent(ctx().copy_stream, g_ev_pf_compute, 0));
+  if (nbytes) SK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx().copy_stream));
+  SK_CUDA(cudaEventRecord(g_ev_pf_done, ctx().copy_stream));
+  return SK_OK;
+}
+int sk_prefetch_wait(void) {
+  if (!ctx().ready || !g_ev_pf_done) return SK_OK;
+  SK_CUDA(cudaStreamWaitEvent(ctx().stream, g_ev_pf_done, 0));
+  return SK_OK;
+}
+
 int sk_d2d(void *dst, const void *src, size_t nbytes) {
   int rc = ensure_init();
   if (rc) return rc;

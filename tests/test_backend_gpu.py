@@ -425,3 +425,26 @@ def test_rng_statistics(sk):
     sk.random.seed(123)
     u2 = sk.asnumpy(sk.random.uniform(-2.0, 3.0, (1000, 1000)))
     assert np.array_equal(u, u2)
+
+
+def test_input_prefetch_on_copy_stream(sk):
+    """PinnedBuffer.prefetch_to_device + prefetch_wait: the copy is ordered after the compute work
+    queued before it (safe reuse of a staging buffer) and visible to the work queued after the
+    wait; two staging buffers, several rounds."""
+    n = 1 << 20
+    pins = [sk.PinnedBuffer((n,), "float32") for _ in range(2)]
+    stage = [sk.empty((n,), "float32") for _ in range(2)]
+    rng = np.random.default_rng(9)
+    got, want = [], []
+    pins[0].array[...] = rng.random(n, dtype=np.float32)
+    pins[0].prefetch_to_device(stage[0])
+    for k in range(6):
+        sk.prefetch_wait()
+        want.append(float(pins[k % 2].array.astype(np.float64).sum()))
+        nxt = (k + 1) % 2
+        sk.synchronize()                       # the host may refill the pinned buffer only after its copy is done
+        pins[nxt].array[...] = rng.random(n, dtype=np.float32)
+        pins[nxt].prefetch_to_device(stage[nxt])
+        heavy = sk.multiply(sk.add(stage[k % 2], 0.0), 1.0)        # compute on the current buffer while the next copies
+        got.append(float(sk.asnumpy(sk.sum(heavy, None, "float32", None, False))))
+    assert np.allclose(got, want, rtol=1e-5)
