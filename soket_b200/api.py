@@ -14,6 +14,7 @@ from soket_b200.engine import (  # noqa: F401
     zeros_like, ones_like, empty_like, rand_like, randn_like,
     log, exp, logsumexp, stack, set_leaf_grad_hook,
 )
-from soket_b200 import nn, optim  # noqa: F401
+from soket_b200 import nn, optim, transforms, utils  # noqa: F401
+import soket_b200.utils.data  # noqa: F401,E402  (soket.utils.data: Dataset, DataLoader, MNIST)
 
 bool = bool_  # soket exports the dtype under the name `bool` (soket/dtype.pyx:137-151)

@@ -20,6 +20,8 @@ __device__ __forceinline__ int64_t load_index(const void *p, int dt, int64_t i) 
   }
 }
 
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
 struct GatherDesc {
   const void *src;
   const void *index;
@@ -110,6 +112,16 @@ int sk_gather_rows(const sk_array *src, const sk_array *index, sk_array *out) {
   SK_REQUIRE(numel(out) == d.n_index * inner, "sk_gather_rows: output size mismatch");
   if (d.n_index * inner == 0) return SK_OK;
   SK_REQUIRE(d.n_rows > 0, "sk_gather_rows: index into an empty axis");
+  // rows that are whole 16-byte units on both sides (MNIST: 784 floats = 196 units) move as uint4
+  const int64_t row_bytes = inner * dtype_size(src->dtype);
+  if (row_bytes % 16 == 0 && (src->strides[0] * dtype_size(src->dtype)) % 16 == 0 &&
+      aligned16(src->data) && aligned16(out->data)) {
+    d.inner = row_bytes / 16;
+    d.src_row_stride = src->strides[0] * dtype_size(src->dtype) / 16;
+    gather_rows_kernel<uint4><<<grid_for(d.n_index * d.inner, 256, 8), 256, 0, stream()>>>(d);
+    SK_LAUNCH_CHECK();
+    return SK_OK;
+  }
   int grid = grid_for(d.n_index * inner, 256, 8);
   switch (dtype_size(src->dtype)) {
     case 1: gather_rows_kernel<uint8_t><<<grid, 256, 0, stream()>>>(d); break;
