@@ -306,6 +306,16 @@ int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
                  double beta1, double beta2, double eps, double weight_decay,
                  double one_minus_beta1_t, double one_minus_beta2_t, int first_step,
                  double grad_scale);
+/* The same update with the running products {beta1^t, beta2^t} (optim.pyx:191-195,266-269)
+ * held as two doubles in DEVICE memory: the kernel forms 1 - beta^t itself (same double
+ * subtraction, same float32 rounding as the host path), sk_adam_bias_advance multiplies them
+ * by the betas after a step.  Nothing step-dependent is left in the kernel arguments, so an
+ * Adam step can be captured in a CUDA graph and replayed. */
+int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *grads,
+                     float *const *m, float *const *v, const int64_t *sizes, double lr,
+                     double beta1, double beta2, double eps, double weight_decay,
+                     const double *bias_state, int first_step, double grad_scale);
+int sk_adam_bias_advance(double *bias_state, double beta1, double beta2);
 
 /* ------------------------------------------------------------- data parallel
  * new (the reference has no collective): NCCL all-reduce(sum) of fp32

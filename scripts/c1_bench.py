@@ -21,6 +21,9 @@ ap.add_argument("--warmup", type=int, default=20)
 ap.add_argument("--variant", default="fn", choices=["fn", "verbatim"])
 ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--graph", action="store_true", help="also time the step as one CUDA-graph launch (soket_b200.graph.StaticStep)")
+ap.add_argument("--loader", action="store_true",
+                help="also time one EPOCH (60 000 samples, 600 steps) fed by the DataLoader: resident gather path, "
+                     "the reference's per-sample path on the GPU device, and the reference's own loader on the CPU")
 args = ap.parse_args()
 DIM, HID, NB, C, B = 784, 100, 3, 10, 100
 rng = np.random.default_rng(0)
@@ -105,6 +108,87 @@ if args.graph:
     out["gpu_graph"] = {"ms_per_step": sec_g * 1e3, "samples_per_s": B / sec_g, "last_loss": last,
                         "launches_per_step": "1 graph + 2 batch copies"}
     g.close()
+
+
+def epoch_through_loader(nn, SGD, kaiming, sync, loader, graph=False):
+    """examples/mlp_resnet/model.py:72-97 (mlp_resnet_epoch, training branch) without the
+    accuracy pass: for X, y in loader: loss = crit(model(X), y); backward; step; loss.item()."""
+    np.random.seed(0)
+    model = ref_model.build_model(nn, DIM, HID, NB, C, norm="layer", drop_prob=0.01, retain_fn=args.variant == "fn")
+    for m in model.modules():
+        if type(m).__name__ == "Linear":
+            kaiming(m.weight)
+    opt = SGD(model.parameters(), lr=0.01)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    model.train(True)
+    g = None
+    if graph:
+        from soket_b200.graph import StaticStep
+        xb, yb = soket.Tensor(X[:B]), soket.Tensor(y[:B])
+
+        def gstep():
+            loss = crit(model(xb), yb)
+            loss.backward()
+            opt.step()
+            return loss
+        g = StaticStep(gstep)
+    total = 0.0
+    for ep in range(2):                       # epoch 0 warms up (allocator, dataset upload); epoch 1 is timed
+        sync()
+        t0 = time.perf_counter()
+        total = 0.0
+        for bx, by in loader:
+            if g is not None:
+                xb._data[:] = bx._data
+                yb._data[:] = by._data
+                g.launch()
+                total += g.loss.item()
+            else:
+                loss = crit(model(bx), by)
+                loss.backward()
+                opt.step()
+                total += loss.item()
+        sync()
+        sec = time.perf_counter() - t0
+    if g is not None:
+        g.close()
+    return {"epoch_s": sec, "samples_per_s": loader.max_iter * B / sec, "steps": loader.max_iter,
+            "mean_loss": total / loader.max_iter}
+
+
+if args.loader:
+    from soket_b200.transforms import ToTensor as GToTensor
+    from soket_b200.utils.data import ArrayDataset, DataLoader as GLoader
+    N = 60000
+    XL = rng.random((N, DIM), dtype=np.float32)
+    yL = rng.integers(0, C, N).astype(np.uint8)
+    ds = ArrayDataset(XL, yL, GToTensor(), GToTensor())
+
+    def arm(name, *a, **kw):
+        try:
+            out[name] = epoch_through_loader(*a, **kw)
+        except Exception as e:                # keep the other arms' numbers
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+    arm("epoch_gpu_resident_loader",
+        gnn, GSGD, gnn.kaiming_normal, sk.synchronize, GLoader(ds, batch_size=B, shuffle=True))
+    arm("epoch_gpu_resident_loader_graph",
+        gnn, GSGD, gnn.kaiming_normal, sk.synchronize, GLoader(ds, batch_size=B, shuffle=True), graph=True)
+    arm("epoch_gpu_per_sample_loader",
+        gnn, GSGD, gnn.kaiming_normal, sk.synchronize, GLoader(ds, batch_size=B, shuffle=True, resident=False))
+    if not args.no_cpu and ref_model.import_reference() is not None:
+        import soket.nn as rnn0
+        from soket.nn.init import kaiming_normal as rkaiming
+        from soket.optim import SGD as RSGD0
+        from soket.transforms import ToTensor as RToTensor
+        from soket.utils.data import DataLoader as RLoader
+
+        class RefArrays(ArrayDataset):        # same samples, the reference's ToTensor (CPU tensors)
+            pass
+        rds = RefArrays(XL, yL, RToTensor(), RToTensor())
+        arm("epoch_cpu_reference_loader",
+            rnn0, RSGD0, rkaiming, lambda: None, RLoader(rds, batch_size=B, shuffle=True))
+        out["epoch_cpu_reference_loader"]["cores"] = os.cpu_count()
+
 if not args.no_cpu:
     ref = ref_model.import_reference()
     if ref is not None:

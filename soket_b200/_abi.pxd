@@ -168,6 +168,11 @@ cdef extern from "soket_b200.h" nogil:
                      double beta1, double beta2, double eps, double weight_decay,
                      double one_minus_beta1_t, double one_minus_beta2_t, int first_step,
                      double grad_scale)
+    int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *grads,
+                         float *const *m, float *const *v, const int64_t *sizes, double lr,
+                         double beta1, double beta2, double eps, double weight_decay,
+                         const double *bias_state, int first_step, double grad_scale)
+    int sk_adam_bias_advance(double *bias_state, double beta1, double beta2)
 
     int sk_nccl_available()
     int sk_nccl_unique_id(char *id)

@@ -194,10 +194,23 @@ def sgd_step(list params, list grads, double lr, double weight_decay=0.0, double
     _check(sk_sgd_step(n, L.p, L.g, L.sizes, lr, weight_decay, grad_scale))
 
 
+cdef double *_bias_ptr(ndarray state) except NULL:
+    if state._code != SK_F64 or state._numel() != 2 or not state._is_contiguous() or state._ptr == 0:
+        raise ValueError('Adam bias state must be a contiguous float64 device array of 2 elements')
+    return <double *> state._ptr
+
+
+def adam_bias_advance(ndarray state, double beta1, double beta2):
+    """state[0] *= beta1; state[1] *= beta2 on the device (optim.pyx:266-267)."""
+    _check(sk_adam_bias_advance(_bias_ptr(state), beta1, beta2))
+
+
 def adam_step(list params, list grads, list m, list v, double lr, double beta1, double beta2,
               double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
-              bint first_step, double grad_scale=1.0):
-    """In-place Adam over all tensors in ONE launch (optim.pyx:201-269)."""
+              bint first_step, double grad_scale=1.0, bias_state=None):
+    """In-place Adam over all tensors in ONE launch (optim.pyx:201-269).  With `bias_state`
+    (device float64 {beta1^t, beta2^t}) the kernel forms the bias corrections itself and the
+    two host scalars are ignored (graph-capturable form)."""
     cdef int n = len(params), i
     cdef _PtrLists L = _PtrLists(n)
     cdef ndarray p, g
@@ -208,6 +221,10 @@ def adam_step(list params, list grads, list m, list v, double lr, double beta1, 
         L.p[i] = _fptr(p); L.g[i] = _fptr(g)
         L.m[i] = _fptr(<ndarray> m[i]); L.v[i] = _fptr(<ndarray> v[i])
         L.sizes[i] = p._numel()
+    if bias_state is not None:
+        _check(sk_adam_step_dev(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
+                                _bias_ptr(<ndarray> bias_state), first_step, grad_scale))
+        return
     _check(sk_adam_step(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
                         one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale))
 

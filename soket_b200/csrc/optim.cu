@@ -35,6 +35,9 @@ struct AdamArgs {
   int n;
   float lr, beta1, beta2, omb1, omb2, eps, wd, bc1, bc2, grad_scale;
   int have_wd, have_scale, first;
+  // capturable variant: {beta1^t, beta2^t} as doubles in DEVICE memory (advanced by
+  // adam_bias_advance_kernel), so that a CUDA-graph replay sees the current bias corrections
+  const double *bias_state;
 };
 
 template <typename A>
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(kOT) sgd_kernel(const __grid_constant__ SgdArg
   }
 }
 
-__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamArgs &a) {
+__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamArgs &a,
+                                         const float bc1, const float bc2) {
   if (a.have_scale) g = __fmul_rn(g, a.grad_scale);
   if (a.have_wd) g = __fadd_rn(g, __fmul_rn(p, a.wd));  // optim.pyx:220-222
   const float gm = __fmul_rn(g, a.omb1);                 // grad * (1 - beta1)
@@ -93,8 +97,8 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
     m = __fadd_rn(__fmul_rn(m, a.beta1), gm);
     v = __fadd_rn(__fmul_rn(v, a.beta2), gv);
   }
-  const float mh = __fdiv_rn(m, a.bc1);  // optim.pyx:246-247
-  const float vh = __fdiv_rn(v, a.bc2);
+  const float mh = __fdiv_rn(m, bc1);  // optim.pyx:246-247
+  const float vh = __fdiv_rn(v, bc2);
   // p - lr * (mh / (pow(vh, 0.5) + eps))   optim.pyx:254-263 ; quirk Q3: maximize is a no-op
   p = __fsub_rn(p, __fmul_rn(a.lr, __fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), a.eps))));
 }
@@ -107,6 +111,10 @@ __global__ void __launch_bounds__(kOT) adam_kernel(const __grid_constant__ AdamA
   float *m = a.m[t];
   float *v = a.v[t];
   const int64_t n = a.size[t];
+  // 1 - beta^t: the host's double subtraction rounded to float32 (optim.pyx:266-269 + NEP 50),
+  // from the kernel arguments or -- capturable -- recomputed identically from device state
+  const float bc1 = a.bias_state ? (float)__dsub_rn(1.0, a.bias_state[0]) : a.bc1;
+  const float bc2 = a.bias_state ? (float)__dsub_rn(1.0, a.bias_state[1]) : a.bc2;
   const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
   if (vec) {
 #pragma unroll
@@ -117,18 +125,24 @@ __global__ void __launch_bounds__(kOT) adam_kernel(const __grid_constant__ AdamA
         float4 gv = ld_stream(reinterpret_cast<const float4 *>(g + i));
         float4 mv = a.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4 *>(m + i);
         float4 vv = a.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4 *>(v + i);
-        adam_one(pv.x, gv.x, mv.x, vv.x, a); adam_one(pv.y, gv.y, mv.y, vv.y, a);
-        adam_one(pv.z, gv.z, mv.z, vv.z, a); adam_one(pv.w, gv.w, mv.w, vv.w, a);
+        adam_one(pv.x, gv.x, mv.x, vv.x, a, bc1, bc2); adam_one(pv.y, gv.y, mv.y, vv.y, a, bc1, bc2);
+        adam_one(pv.z, gv.z, mv.z, vv.z, a, bc1, bc2); adam_one(pv.w, gv.w, mv.w, vv.w, a, bc1, bc2);
         *reinterpret_cast<float4 *>(p + i) = pv;
         *reinterpret_cast<float4 *>(m + i) = mv;
         *reinterpret_cast<float4 *>(v + i) = vv;
       } else {
-        for (int64_t k = i; k < n && k < i + 4; ++k) adam_one(p[k], g[k], m[k], v[k], a);
+        for (int64_t k = i; k < n && k < i + 4; ++k) adam_one(p[k], g[k], m[k], v[k], a, bc1, bc2);
       }
     }
   } else {
-    for (int64_t i = base + threadIdx.x; i < n && i < base + kChunk; i += kOT) adam_one(p[i], g[i], m[i], v[i], a);
+    for (int64_t i = base + threadIdx.x; i < n && i < base + kChunk; i += kOT) adam_one(p[i], g[i], m[i], v[i], a, bc1, bc2);
   }
+}
+
+// optim.pyx:266-267: beta1_t *= beta1; beta2_t *= beta2 (Python floats = IEEE doubles)
+__global__ void adam_bias_advance_kernel(double *state, double beta1, double beta2) {
+  state[0] = __dmul_rn(state[0], beta1);
+  state[1] = __dmul_rn(state[1], beta2);
 }
 
 }  // namespace sk
@@ -169,10 +183,11 @@ int sk_sgd_step(int n_tensors, float *const *params, const float *const *grads, 
   return SK_OK;
 }
 
-int sk_adam_step(int n_tensors, float *const *params, const float *const *grads, float *const *m,
-                 float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
-                 double eps, double weight_decay, double one_minus_beta1_t,
-                 double one_minus_beta2_t, int first_step, double grad_scale) {
+static int adam_step_impl(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                          float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, double one_minus_beta1_t,
+                          double one_minus_beta2_t, int first_step, double grad_scale,
+                          const double *bias_state) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || (params && grads && m && v && sizes)), "sk_adam_step: null list");
@@ -198,6 +213,7 @@ int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
     a.bc1 = (float)one_minus_beta1_t; a.bc2 = (float)one_minus_beta2_t;
     a.grad_scale = (float)grad_scale;
     a.have_wd = weight_decay != 0.0; a.have_scale = grad_scale != 1.0; a.first = first_step;
+    a.bias_state = bias_state;
     if (blocks == 0) continue;
     double elems = 0;
     for (int k = 0; k < n; ++k) elems += (double)a.size[k];
@@ -205,6 +221,32 @@ int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
     adam_kernel<<<blocks, kOT, 0, stream()>>>(a);
     SK_LAUNCH_CHECK();
   }
+  return SK_OK;
+}
+
+int sk_adam_step(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                 float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                 double eps, double weight_decay, double one_minus_beta1_t,
+                 double one_minus_beta2_t, int first_step, double grad_scale) {
+  return adam_step_impl(n_tensors, params, grads, m, v, sizes, lr, beta1, beta2, eps, weight_decay,
+                        one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale, nullptr);
+}
+
+int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                     float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                     double eps, double weight_decay, const double *bias_state, int first_step,
+                     double grad_scale) {
+  SK_REQUIRE(bias_state, "sk_adam_step_dev: null bias state");
+  return adam_step_impl(n_tensors, params, grads, m, v, sizes, lr, beta1, beta2, eps, weight_decay,
+                        0.0, 0.0, first_step, grad_scale, bias_state);
+}
+
+int sk_adam_bias_advance(double *bias_state, double beta1, double beta2) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(bias_state, "sk_adam_bias_advance: null bias state");
+  adam_bias_advance_kernel<<<1, 1, 0, stream()>>>(bias_state, beta1, beta2);
+  SK_LAUNCH_CHECK();
   return SK_OK;
 }
 

@@ -20,8 +20,10 @@ What makes a replay equal to an eager step:
     Python-visible tensors (params, their .grad, the loss) are the graph's own buffers;
   * dropout draws a fresh mask per replay: the kernels mix a device-side epoch counter into
     their seeds at run time and the graph's first node advances it;
-  * the optimiser's scalars must not change from step to step: SGD qualifies; Adam's bias
-    corrections are host floats (optim.pyx:191-195) and would be frozen, so Adam is refused.
+  * the optimiser's kernel arguments must not change from step to step: SGD qualifies as is;
+    Adam's bias corrections are host floats in the reference (optim.pyx:191-195) and would be
+    frozen, so the default Adam is refused and ``Adam(..., capturable=True)`` keeps beta^t in
+    device memory instead (same update, bit for bit; tests/test_graph_gpu.py).
 """
 from __future__ import annotations
 

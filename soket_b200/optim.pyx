@@ -9,6 +9,8 @@ fresh array per parameter: optim.pyx:131,254) and Adam's moments stay resident.
 `grad_scale` folds the 1/W of data-parallel gradient averaging into the same
 kernel.
 """
+import numpy as np
+
 from soket_b200.engine cimport Tensor
 from soket_b200 import _core as B
 from soket_b200 import _fused as F
@@ -77,8 +79,14 @@ cdef class Adam(Optimizer):
     cdef public bint _have_weight_decay
     cdef public object _t, _beta1_t, _beta2_t, _one_minus_beta1_t, _one_minus_beta2_t
     cdef public list _u, _v
+    cdef public bint _capturable
+    cdef public object _bias_dev
 
-    def __init__(self, params, lr=0.001, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, maximize=False):
+    def __init__(self, params, lr=0.001, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, maximize=False,
+                 capturable=False):
+        """`capturable=True` (not in the reference): the running products beta1^t, beta2^t live in
+        device memory and are advanced by a kernel, so `step()` may be captured in a CUDA graph
+        (soket_b200.graph.StaticStep).  The update is bit-identical to the default form."""
         Optimizer.__init__(self, params)
         if len(betas) < 2:
             raise ValueError('Invalid betas!')
@@ -97,16 +105,25 @@ cdef class Adam(Optimizer):
         self._one_minus_beta2_t = 1.0 - self._beta2_t
         self._u = [None] * len(self._params)
         self._v = [None] * len(self._params)
+        self._capturable = bool(capturable)
+        self._bias_dev = None
+        if self._capturable:
+            self._bias_dev = B.array(np.array([self._beta1_t, self._beta2_t], dtype=np.float64))
 
     def step(self):
-        if B.is_capturing():
+        if B.is_capturing() and not self._capturable:
             raise RuntimeError("Adam.step inside a CUDA-graph capture: the bias corrections 1 - beta^t are host "
-                               "scalars (optim.pyx:191-195) and would be frozen in the graph; capture SGD steps only")
+                               "scalars (optim.pyx:191-195) and would be frozen in the graph; construct the "
+                               "optimizer with Adam(..., capturable=True) or capture SGD steps only")
         ps, gs, idx = self._live()
         # first-step parameters (no state yet) and the rest go to separate launches:
         # optim.pyx:224-238 initialises m, v without the beta * 0 term
         fresh = [k for k, i in enumerate(idx) if self._u[i] is None]
         seen = [k for k, i in enumerate(idx) if self._u[i] is not None]
+        if fresh and B.is_capturing():
+            raise RuntimeError("Adam.step inside a CUDA-graph capture met a parameter without optimizer state: "
+                               "its first-step form (optim.pyx:224-238) would be replayed forever; run one eager "
+                               "step first (StaticStep's dry runs do)")
         for k in fresh:
             i = idx[k]
             self._u[i] = B.empty(ps[k].shape, 'float32')
@@ -118,7 +135,12 @@ cdef class Adam(Optimizer):
             F.adam_step([ps[k] for k in group], [gs[k] for k in group],
                         [self._u[idx[k]] for k in group], [self._v[idx[k]] for k in group],
                         self._lr, self._beta1, self._beta2, self._eps, wd,
-                        self._one_minus_beta1_t, self._one_minus_beta2_t, first, self.grad_scale)
+                        self._one_minus_beta1_t, self._one_minus_beta2_t, first, self.grad_scale,
+                        self._bias_dev)
+        if self._capturable:
+            # the device copy is what the kernels read; the host mirrors below only follow the
+            # steps issued through this method (graph replays advance the device copy alone)
+            F.adam_bias_advance(self._bias_dev, self._beta1, self._beta2)
         self._t += 1
         self._beta1_t *= self._beta1
         self._beta2_t *= self._beta2

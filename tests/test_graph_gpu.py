@@ -107,3 +107,78 @@ def test_graph_capture_refuses_adam(sk):
         StaticStep(step)
     # the engine is still usable afterwards
     assert np.isfinite(step().item())
+
+
+def test_capturable_adam_graph_replay_equals_eager_default_adam(sk):
+    """Adam(capturable=True) keeps beta^t on the device (sk_adam_step_dev / sk_adam_bias_advance):
+    a replayed step must equal the DEFAULT Adam's eager step bit for bit -- losses through ten
+    steps and every parameter at the end -- weight decay included."""
+    import soket_b200.api as soket
+    from soket_b200.graph import StaticStep
+    from soket_b200.optim import Adam
+    rng = np.random.default_rng(4)
+    Xs = rng.random((8, B, DIM), dtype=np.float32)
+    ys = rng.integers(0, C, (8, B)).astype(np.uint8)
+    order = [0, 0, 0] + list(range(1, 8))
+
+    model, _, crit = build(sk, 0.0, 0.0)
+    opt = Adam(model.parameters(), lr=1e-3, weight_decay=0.01)
+    want = []
+    for i in order:
+        loss = crit(model(soket.Tensor(Xs[i])), soket.Tensor(ys[i]))
+        loss.backward()
+        opt.step()
+        want.append(loss.item())
+    want_params = [p.numpy() for p in model.parameters()]
+
+    model, _, crit = build(sk, 0.0, 0.0)
+    opt = Adam(model.parameters(), lr=1e-3, weight_decay=0.01, capturable=True)
+    xb, yb = soket.Tensor(Xs[0]), soket.Tensor(ys[0])
+
+    def step():
+        loss = crit(model(xb), yb)
+        loss.backward()
+        opt.step()
+        return loss
+    g = StaticStep(step)
+    got = [None, None, g.loss.item()]
+    for i in range(1, 8):
+        xb._data[:] = sk.array(Xs[i])
+        yb._data[:] = sk.array(ys[i])
+        g.launch()
+        got.append(g.loss.item())
+    assert got[2:] == want[2:], (got, want)
+    for p, w in zip(model.parameters(), want_params):
+        assert p.numpy().tobytes() == w.tobytes()
+    # the device-side products are beta^(t+1) after t steps, as the host recurrence gives them
+    b1, b2 = 0.9, 0.999
+    h1, h2 = b1, b2
+    for _ in order:
+        h1 *= b1
+        h2 *= b2
+    assert sk.asnumpy(opt._bias_dev).tolist() == [h1, h2]
+    g.close()
+
+
+def test_capturable_adam_eager_equals_default_adam(sk):
+    """No graph involved: the two forms of the kernel argument give identical updates."""
+    import soket_b200.api as soket
+    from soket_b200.optim import Adam
+    rng = np.random.default_rng(5)
+    shapes = [(33, 17), (17,), (1000, 3)]
+    init = [rng.standard_normal(s).astype("float32") for s in shapes]
+    grads = [[rng.standard_normal(s).astype("float32") for s in shapes] for _ in range(4)]
+    finals = []
+    for capturable in (False, True):
+        ps = [soket.Tensor(w.copy(), requires_grad=True) for w in init]
+        opt = Adam(ps, lr=1e-2, capturable=capturable)
+        for step_grads in grads:
+            loss = None
+            for p, gr in zip(ps, step_grads):
+                term = (p * soket.Tensor(gr)).sum()
+                loss = term if loss is None else loss + term
+            loss.backward()
+            opt.step()
+        finals.append([p.numpy() for p in ps])
+    for a, b in zip(*finals):
+        assert a.tobytes() == b.tobytes()
