@@ -122,6 +122,15 @@ def _dt(x):
 
 
 # ============================================================================ device
+import enum as _enum
+
+
+class DeviceType(_enum.IntEnum):
+    """soket/backend/device.pxd:10-13."""
+    CPU = 0
+    GPU = 1
+
+
 class Device:
     """soket/backend/device.pyx:33-249, GPU branch only: this package IS the GPU
     backend; CPU tensors belong to the reference's NumPy path."""
@@ -132,7 +141,7 @@ class Device:
 
     @property
     def type(self):
-        return 'gpu'
+        return DeviceType.GPU       # device.pyx:166-170
 
     @property
     def id(self):
@@ -173,6 +182,42 @@ def gpu(id=None):
     if id is None or id == 0:
         return _gpu0
     return Device(id)
+
+
+def cpu():
+    """device.pyx:270-272 returns the NumPy device; this package is the GPU device only."""
+    raise RuntimeError('soket_b200 implements the GPU device only: CPU tensors belong to the reference\'s '
+                       'NumPy backend (soket.cpu())')
+
+
+# ---- lazy mode (tensor.pyx:24-51) -----------------------------------------------------------
+# The reference's lazy() only postpones Tensor._compute_data() until a value is needed; results
+# are the same.  This engine always evaluates at construction (an admissible schedule of the
+# same graph), so the switch is accepted and remembered but changes nothing.
+_LAZY_STATE = False
+
+
+class LazyState:
+    def __enter__(self):
+        global _LAZY_STATE
+        self._previous = _LAZY_STATE
+        _LAZY_STATE = True
+
+    def __exit__(self, *exc):
+        global _LAZY_STATE
+        _LAZY_STATE = self._previous
+        return False
+
+
+def lazy(enabled=None):
+    global _LAZY_STATE
+    if enabled is None:
+        return LazyState()
+    _LAZY_STATE = bool(enabled)
+
+
+def lazy_enabled():
+    return _LAZY_STATE
 
 
 def _default_device():
@@ -990,6 +1035,9 @@ def zeros_like(Tensor t, device=None, dtype=None, requires_grad=False):
 def ones_like(Tensor t, device=None, dtype=None, requires_grad=False):
     dt = t._dtype if dtype is None else _dt(dtype)
     return _mk(B.ones(t.shape, dt.name), dt, requires_grad)
+
+
+one_like = ones_like      # the reference exports it under this name (creation.pyx:289)
 
 
 def empty_like(Tensor t, device=None, dtype=None, requires_grad=False):

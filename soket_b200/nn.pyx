@@ -497,6 +497,23 @@ class init:
         tensor.data = E.rand(tensor.shape, low=-bound, high=bound, dtype=tensor.dtype)
 
 
+
+# soket.nn.init and soket.nn.functional are modules in the reference (`from soket.nn.init import
+# kaiming_normal`, `soket.nn.functional.layer_norm`); this file is one extension module, so the two
+# namespaces are registered as importable modules of it.
+def _submodule(name, members):
+    import sys
+    import types
+    mod = types.ModuleType('soket_b200.nn.' + name)
+    mod.__dict__.update(members)
+    sys.modules['soket_b200.nn.' + name] = mod
+    return mod
+
+
+functional = _submodule('functional', {'batch_norm': E.batch_norm, 'layer_norm': E.layer_norm})
+_submodule('init', {k: getattr(init, k) for k in ('xavier_normal', 'xavier_uniform', 'kaiming_normal',
+                                                   'kaiming_uniform')})
+
 kaiming_normal = init.kaiming_normal
 kaiming_uniform = init.kaiming_uniform
 xavier_normal = init.xavier_normal

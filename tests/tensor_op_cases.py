@@ -1,0 +1,104 @@
+"""Tensor-level op cases shared by the reference (oracle/_ref, CPU) and soket_b200 (GPU):
+each case is (name, input shapes, fn(soket, *tensors) -> Tensor).  `soket` is the namespace
+under test (the built reference's `soket` or `soket_b200.api`); the bodies use only the public
+Tensor API of soket/tensor/tensor.pyx, so the same code runs on both.  SURVEY.md section 8(a)
+"Tensor-level methods on the path" + section 8(f)-3."""
+import numpy as np
+
+
+def _t(soket, a):
+    return soket.Tensor(np.asarray(a))
+
+
+CASES = [
+    # ---- elementwise, tensor (x) tensor with broadcasting (tensor.pyx:1101-1583) -----------
+    ("add_bcast_row", [(5, 7), (7,)], lambda s, a, b: a + b),
+    ("add_bcast_col", [(5, 7), (5, 1)], lambda s, a, b: a + b),
+    ("add_bcast_both", [(5, 1, 4), (3, 1)], lambda s, a, b: a + b),
+    ("sub", [(4, 6), (4, 6)], lambda s, a, b: a - b),
+    ("sub_bcast", [(6,), (4, 6)], lambda s, a, b: a - b),
+    ("mul", [(4, 6), (4, 6)], lambda s, a, b: a * b),
+    ("mul_bcast_scalar_like", [(4, 6), (1, 1)], lambda s, a, b: a * b),
+    ("div", [(4, 6), (4, 6)], lambda s, a, b: a / (b * b + 1.0)),
+    ("div_bcast", [(4, 6), (6,)], lambda s, a, b: a / (b * b + 0.5)),
+    ("pow_tensor", [(3, 5), (3, 5)], lambda s, a, b: (a * a + 0.5) ** b),
+    ("neg", [(3, 5)], lambda s, a: -a),
+    # ---- scalar operands, both sides (tensor.pyx:231-237, _rsub/_rdiv/_rpow) ------------
+    ("add_scalar", [(3, 5)], lambda s, a: a + 2.5),
+    ("radd_scalar", [(3, 5)], lambda s, a: 2.5 + a),
+    ("sub_scalar", [(3, 5)], lambda s, a: a - 1.25),
+    ("rsub_scalar", [(3, 5)], lambda s, a: 1.25 - a),
+    ("mul_scalar_int", [(3, 5)], lambda s, a: a * 3),
+    ("rmul_scalar", [(3, 5)], lambda s, a: 0.5 * a),
+    ("div_scalar", [(3, 5)], lambda s, a: a / 4.0),
+    ("rdiv_scalar", [(3, 5)], lambda s, a: 2.0 / (a * a + 1.0)),
+    ("pow_scalar", [(3, 5)], lambda s, a: (a * a + 0.5) ** 1.5),
+    ("pow_scalar_int", [(3, 5)], lambda s, a: a ** 3),
+    ("rpow_scalar", [(3, 5)], lambda s, a: 2.0 ** a),
+    # ---- reductions (tensor.pyx:1680-1822) ----------------------------------------------------
+    ("sum_all", [(4, 5, 6)], lambda s, a: a.sum()),
+    ("sum_axis0", [(4, 5, 6)], lambda s, a: a.sum(0)),
+    ("sum_axis_last_keep", [(4, 5, 6)], lambda s, a: a.sum(-1, keepdims=True)),
+    ("sum_axes_02", [(4, 5, 6)], lambda s, a: a.sum(0, 2)),
+    ("sum_axes_tuple", [(4, 5, 6)], lambda s, a: a.sum((1, 2))),
+    ("mean_axis1", [(4, 5, 6)], lambda s, a: a.mean(1)),
+    ("mean_axis0_keep", [(4, 5, 6)], lambda s, a: a.mean(0, keepdims=True)),
+    ("mean_all", [(4, 5)], lambda s, a: a.mean()),
+    ("max_axis1", [(4, 5, 6)], lambda s, a: a.max(1)),
+    ("max_keep", [(4, 5, 6)], lambda s, a: a.max(-1, keepdims=True)),
+    ("max_all", [(4, 5)], lambda s, a: a.max()),
+    ("min_axis0", [(4, 5, 6)], lambda s, a: a.min(0)),
+    ("min_axes_keep", [(4, 5, 6)], lambda s, a: a.min(0, 2, keepdims=True)),
+    ("logsumexp_last", [(6, 10)], lambda s, a: s.logsumexp(a, -1)),
+    ("logsumexp_keep", [(6, 10)], lambda s, a: s.logsumexp(a, 1, keepdims=True)),
+    ("logsumexp_all", [(3, 4)], lambda s, a: s.logsumexp(a)),
+    ("log_exp", [(3, 5)], lambda s, a: s.log(s.exp(a) + 1.0)),
+    # ---- shape ops (tensor.pyx:1629, 1863-1977) ---------------------------------------------
+    ("broadcast_to", [(1, 5)], lambda s, a: a.broadcast_to(4, 3, 5)),
+    ("broadcast_to_tuple", [(3, 1)], lambda s, a: a.broadcast_to((3, 6))),
+    ("reshape", [(4, 6)], lambda s, a: a.reshape(2, 12)),
+    ("reshape_of_transpose", [(4, 6)], lambda s, a: a.T.reshape(3, 8)),
+    ("permute", [(2, 3, 4)], lambda s, a: a.permute(2, 0, 1)),
+    ("permute_then_mul", [(2, 3, 4), (4, 2, 3)], lambda s, a, b: a.permute(2, 0, 1) * b),
+    ("transpose_reverses_all_axes", [(2, 3, 4)], lambda s, a: a.transpose()),
+    ("T_matmul", [(5, 3), (5, 4)], lambda s, a, b: a.T @ b),
+    # ---- indexing (tensor.pyx:1979, 922) -------------------------------------------------------
+    ("getitem_int", [(4, 6)], lambda s, a: a[2]),
+    ("getitem_neg_int", [(4, 6)], lambda s, a: a[-1]),
+    ("getitem_slice", [(6, 8)], lambda s, a: a[1:5:2]),
+    ("getitem_tuple", [(6, 8)], lambda s, a: a[1:5, ::3]),
+    ("getitem_int_slice", [(4, 5, 6)], lambda s, a: a[1, :, 2:5]),
+    ("getitem_chain", [(4, 5, 6)], lambda s, a: a[1:][0] * 2.0),
+    # ---- matmul (tensor.pyx:1824) -------------------------------------------------------------
+    ("matmul_2d", [(7, 5), (5, 3)], lambda s, a, b: a @ b),
+    ("matmul_batched", [(2, 4, 5), (2, 5, 3)], lambda s, a, b: a @ b),
+    ("matmul_bcast_batch", [(3, 2, 4, 5), (5, 6)], lambda s, a, b: a @ b),
+    ("matmul_bcast_batch_lhs", [(4, 5), (3, 5, 2)], lambda s, a, b: a @ b),
+    # ---- composites -----------------------------------------------------------------------------
+    ("softmax", [(6, 10)], lambda s, a: s.exp(a - a.max(-1, keepdims=True)) /
+        s.exp(a - a.max(-1, keepdims=True)).sum(-1, keepdims=True)),
+    ("reuse_of_a_node", [(4, 4)], lambda s, a: (a * a + a) * a - a.sum(0)),
+    ("diamond", [(3, 4), (4,)], lambda s, a, b: ((a + b) * (a - b)).sum(1) + (a * b).mean(1)),
+    ("stack_no_grad", [(3, 4), (3, 4)], lambda s, a, b: s.stack([a, b], axis=1)),
+]
+
+# forward-only cases: integer / bool results, never differentiable (tensor.pyx:812-920, 2050-2338)
+INT_CASES = [
+    ("argmax_last", [(6, 10)], lambda s, a: a.argmax(-1)),
+    ("argmax_axis0_keep", [(6, 10)], lambda s, a: a.argmax(0, keepdims=True)),
+    ("argmax_all", [(3, 4)], lambda s, a: a.argmax()),
+    ("argmin_axis1", [(6, 10)], lambda s, a: a.argmin(1)),
+    ("eq", [(4, 5), (4, 5)], lambda s, a, b: (a * 0 + 1.0) == (b * 0 + 1.0)),
+    ("ne_scalar", [(4, 5)], lambda s, a: a != 0.0),
+    ("gt", [(4, 5), (5,)], lambda s, a, b: a > b),
+    ("ge_scalar", [(4, 5)], lambda s, a: a >= 0.25),
+    ("lt", [(4, 5), (4, 1)], lambda s, a, b: a < b),
+    ("le_is_ge_quirk_q6", [(4, 5), (4, 5)], lambda s, a, b: a <= b),
+    ("one_hot", [(7,)], lambda s, a: s.one_hot(_t(s, np.array([1, 0, 3, 2, 2, 0, 3], "uint8")), 4)),
+    ("one_hot_infer_classes", [(7,)], lambda s, a: s.one_hot(_t(s, np.array([1, 0, 3, 2, 2, 0, 5], "int32")))),
+]
+
+
+def make_inputs(shapes, seed):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal(shp).astype("float32") for shp in shapes]

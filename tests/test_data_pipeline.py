@@ -250,7 +250,8 @@ def test_epoch_loop_through_the_loader_matches_oracle(sk):
     crit = nn.SoftmaxCrossEntropyLoss()
     np.random.seed(5)
     loader = DataLoader(ArrayDataset(X, y), batch_size=100, shuffle=True)
-    for (xb, yb), order in zip(loader, loader.ordering):
+    batches = iter(loader)                       # shuffling loaders draw `ordering` here (loader.py:56-60)
+    for (xb, yb), order in zip(batches, loader.ordering):
         loss = crit(model(xb), yb)
         loss.backward()
         opt.step()

@@ -76,3 +76,45 @@ def test_rendezvous_world_size_2():
     assert out[0][1] == out[1][1] == bytes(range(128))
     assert out[0][2] == out[1][2] == [1.5, 2.5]
     assert out[0][3] == slice(0, 32) and out[1][3] == slice(32, 64)
+
+
+def test_public_api_covers_the_reference(ref_soket):
+    """Every public name a Soket script can reach -- soket.*, soket.nn.*, soket.optim.*,
+    soket.nn.init / functional, Tensor / Module / optimizer attributes -- exists here
+    (submodule names and imports the reference leaks through `import *` aside)."""
+    import soket.nn as rnn
+    import soket.nn.functional as rfun
+    import soket.nn.init as rinit
+    import soket.optim as ropt
+    import soket.transforms as rtf
+    import soket.utils.data as rdata
+    import soket_b200.api as mine
+    import soket_b200.nn.functional as mfun
+    import soket_b200.nn.init as minit
+    from soket_b200 import nn as mnn, optim as mopt, transforms as mtf
+    from soket_b200.utils import data as mdata
+
+    def pub(o):
+        return {n for n in dir(o) if not n.startswith('_')}
+    leaked = {'Sequence', 'autodiff', 'backend', 'creation', 'cupy', 'cupy_device', 'detached', 'device', 'dtype',
+              'np', 'numpy', 'ops', 'tensor', 'util', 'warnings', 'module', 'prototypes', 'Tuple', 'soket',
+              'dataset', 'loader', 'datasets', 'Optional', 'Callable', 'List', 'ceil', 'Dataset_', 'ABC',
+              'abstractmethod'}
+    assert pub(ref_soket) - pub(mine) - leaked == set()
+    assert pub(rnn) - pub(mnn) - leaked == set()
+    assert pub(ropt) - pub(mopt) - leaked == set()
+    assert pub(rinit) - pub(minit) - leaked == set()
+    assert pub(rfun) - pub(mfun) - leaked == set()
+    assert pub(rtf) - pub(mtf) - leaked - {'Tensor'} == set()
+    assert pub(rdata) - pub(mdata) - leaked == set()
+    assert pub(ref_soket.Tensor) - pub(mine.Tensor) == set()
+    assert pub(rnn.Module) - pub(mnn.Module) == set()
+    for cls in ('Identity', 'Linear', 'Sequential', 'Residual', 'ReLU', 'SoftmaxCrossEntropyLoss', 'BatchNorm1d',
+                'BatchNorm2d', 'BatchNorm3d', 'LayerNorm', 'Dropout'):
+        assert pub(getattr(rnn, cls)) - pub(getattr(mnn, cls)) == set(), cls
+    for cls in ('Optimizer', 'SGD', 'Adam'):
+        assert pub(getattr(ropt, cls)) - pub(getattr(mopt, cls)) == set(), cls
+    assert pub(ref_soket.Device) - pub(mine.Device) == set()
+    assert int(mine.DeviceType.GPU) == int(ref_soket.DeviceType.GPU) and mine.gpu().type == mine.DeviceType.GPU
+    with mine.lazy():
+        pass
