@@ -939,7 +939,9 @@ cdef void _finalize_leaf(Tensor n):
     g = _sum_partials(n._partials)
     g = _unbroadcast(g, n.shape)
     n._partials = None
-    n._grad = Tensor._const(g, None, False)   # overwritten, never accumulated (autodiff.pyx:221-222)
+    # overwritten, never accumulated (autodiff.pyx:221-222).  The dtype TAG is the tensor's own: every
+    # backward fn wraps its result with the input's dtype (backward.pyx:14-24), whatever the data is (Q11)
+    n._grad = Tensor._const(g, n._dtype, False)
     if _leaf_hook is not None:
         _leaf_hook(n)
 
@@ -975,7 +977,7 @@ cdef void _compute_gradient(Tensor root, object seed):
                 i._partials.append((gi, gi is not g))
             if i._pending == 0 and i._op is None and len(i._partials):
                 _finalize_leaf(i)
-        n._grad = Tensor._const(g, None, False) if n._retain_grad else None
+        n._grad = Tensor._const(g, n._dtype, False) if n._retain_grad else None
 
 
 # ============================================================================ creation fns

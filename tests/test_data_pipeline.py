@@ -251,7 +251,9 @@ def test_epoch_loop_through_the_loader_matches_oracle(sk):
     np.random.seed(5)
     loader = DataLoader(ArrayDataset(X, y), batch_size=100, shuffle=True)
     batches = iter(loader)                       # shuffling loaders draw `ordering` here (loader.py:56-60)
-    for (xb, yb), order in zip(batches, loader.ordering):
+    for i in range(loader.max_iter):             # (zip() would call iter() again and reshuffle)
+        xb, yb = next(batches)
+        order = loader.ordering[i]
         loss = crit(model(xb), yb)
         loss.backward()
         opt.step()

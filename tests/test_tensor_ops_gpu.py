@@ -75,7 +75,11 @@ def test_forward_and_backward_match_reference(sk, case):
         key = f"{name}/grad{i}"
         if key in GOLD.files:
             assert x.grad is not None, key
-            close(x.grad.numpy(), GOLD[key], key)
+            # quirk Q11 (backward.pyx:676-690): max/min backward divides by an int64 count, so the
+            # gradient DATA is float64 under a float32 dtype tag on both backends; the fixture
+            # holds it rounded to the tag's dtype, as Tensor.__setitem__ delivered it
+            assert str(x.grad.dtype) == GOLD[key].dtype.name, key
+            close(x.grad.numpy().astype(GOLD[key].dtype), GOLD[key], key)
         else:
             assert x.grad is None, key
 
