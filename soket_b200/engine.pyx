@@ -689,11 +689,14 @@ cdef class Tensor:
     def broadcast_to(self, *shape):
         shape = _proper_shape(shape)
         cdef tuple s = self.shape
-        if len(shape) < len(s):
-            raise ValueError('Invalid broadcast shape!')
+        if len(shape) < len(s):     # tensor.pyx:1638-1642
+            raise RuntimeError('Attempt to reduce a tensor using broadcast_to()')
+        for d in shape:
+            if type(d) is not int:
+                raise TypeError('Expected broadcast shape to be integers!')
         for i in range(1, len(s) + 1):
             if s[-i] != shape[-i] and s[-i] != 1:
-                raise ValueError('Invalid broadcast shape!')
+                raise RuntimeError('Incompatible broadcast shapes!')   # tensor.pyx:1664-1666
         return Tensor._from_op(_BroadcastTo(), (self,), B.broadcast_to(self._data, shape), self._dtype)
 
     def sum(self, *axes, dtype=None, keepdims=False):
@@ -831,6 +834,12 @@ cdef class Tensor:
     def __getitem__(self, idx):
         if isinstance(idx, Tensor):
             idx = (<Tensor> idx)._data
+        # tensor.pyx:1994-2016: integer indices are bounds-checked per leading axis -> ValueError
+        cdef tuple s = self.shape
+        items = idx if type(idx) is tuple else (idx,)
+        for k in range(len(items)):
+            if type(items[k]) is int and k < len(s) and (items[k] < -s[k] or items[k] >= s[k]):
+                raise ValueError(f'Select index out of bounds - {items[k]}')
         return Tensor._from_op(_Select(idx), (self,), self._data[idx], self._dtype)
 
     def __setitem__(self, idx, value):
@@ -1154,9 +1163,16 @@ def layer_norm(Tensor X, weight=None, bias=None, eps=1e-5, bint relu=False, resi
         if p is not None and (<Tensor> p)._dtype != X._dtype:
             raise RuntimeError('Input and parameters should share same datatype!')
     cdef ndarray xd = X._data
-    if xd.ndim != 2 or not xd.is_contiguous:
-        xd = B.ascontiguousarray(B.reshape(xd, (X.shape[0], -1)))
+    # functional.pyx:108-114: statistics run over ALL non-batch axes and gamma / beta broadcast against
+    # the trailing axes; the fused kernel covers the 2-D case (one parameter per normalised element)
+    if xd.ndim != 2:
+        return _layer_norm_unfused(X, weight, bias, eps, relu, residual)
+    if not xd.is_contiguous:
+        xd = B.ascontiguousarray(xd)
     cols = xd.shape[1]
+    for p in (weight, bias):
+        if p is not None and (<Tensor> p)._data.size != cols:
+            return _layer_norm_unfused(X, weight, bias, eps, relu, residual)
     if X._dtype.name != 'float32' or cols % 4 != 0 or cols > 8192:
         return _layer_norm_unfused(X, weight, bias, eps, relu, residual)
     rd = None

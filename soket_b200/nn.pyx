@@ -217,8 +217,12 @@ cdef class LayerNorm(Module):
             out = residual + out
         return E.relu_(out) if relu else out
 
-    def __str__(self):
-        return f'soket.nn.LayerNorm({self._normalized_shape}, eps={self._eps})'
+    def __str__(self):    # prototypes.pyx:702-720
+        gamma = self._storage[0]
+        affine = gamma is not None and gamma.requires_grad
+        dtype = gamma.dtype.name if gamma is not None else 'float32'
+        return (f'soket.nn.LayerNorm({self._normalized_shape}, eps={self._eps}, elementwise_affine={affine}, '
+                f'dtype={dtype}, device=GPU:0)')
 
 
 cdef class _BatchNormBase(Module):
