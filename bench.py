@@ -41,6 +41,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line (the driver parses it): keep a private handle to the real
+# stdout and point fd 1 at stderr, so that banners printed by libraries at the C level (e.g.
+# "NCCL version ..." when NCCL_DEBUG is set in the environment) cannot land in front of it.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 DIM, HIDDEN, BLOCKS, CLASSES = 784, 4096, 8, 10
 BATCH_PER_GPU = 8192
 DROP_P = 0.01
@@ -221,7 +227,7 @@ def run_reference(args, env):
                                    f"full-batch CPU throughput is ~15 % higher); NumPy/OpenBLAS threads = all host cores"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def workload_config(args, world):
@@ -445,7 +451,7 @@ def run_ours(args, env):
                 "sample": f"1 Adam step of the same model on {args.cpu_sample_batch} rows after 1 warm-up step "
                           f"(full batch is {batch}; the fixed per-step Adam cost is amortised over the sample, full-batch "
                           f"CPU throughput is ~15 % higher); NumPy/OpenBLAS threads = all host cores"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     ddp.close()
 
 
