@@ -945,6 +945,10 @@ cdef object _binary(int op, object x, object y, object dtype):
     cdef bint is_cmp = op >= SK_OP_EQ
     cdef bint xs = _is_pyscalar(x), ys = _is_pyscalar(y)
     cdef object rdt
+    if op == SK_OP_DIV and dtype is not None and _code(dtype) < SK_F16:
+        # numpy.divide has float loops only: a non-float `dtype=` is rejected (this is what a Soket
+        # true-divide of two integer tensors hits on the reference's CPU backend, forward.pyx:75,85)
+        raise TypeError('No loop matching the specified signature and casting was found for ufunc divide')
     if xs and ys:
         x = np.asarray(x)
         xs = False
@@ -960,6 +964,9 @@ cdef object _binary(int op, object x, object y, object dtype):
             if op == SK_OP_DIV and rdt.kind in 'iub':
                 rdt = _F64
             code = _code(rdt)
+        if op == SK_OP_SUB and code == SK_BOOL:
+            raise TypeError('numpy boolean subtract, the `-` operator, is not supported, use the bitwise_xor, '
+                            'the `^` operator, or the logical_xor function instead.')
         out = _new_array(a._ndim, a._shape, code)
         a._desc(&da)
         out._desc(&dout)
@@ -981,6 +988,9 @@ cdef object _binary(int op, object x, object y, object dtype):
         if op == SK_OP_DIV and rdt.kind in 'iub':
             rdt = _F64
         code = _code(rdt)
+    if op == SK_OP_SUB and code == SK_BOOL:
+        raise TypeError('numpy boolean subtract, the `-` operator, is not supported, use the bitwise_xor, '
+                        'the `^` operator, or the logical_xor function instead.')
     _bcast_shape(a, b, shp, &nd)
     out = _new_array(nd, shp, code)
     a._desc_bcast(&da, nd, shp)

@@ -33,7 +33,7 @@ def weights_for(shape, name):
 
 def run_case(index, out_path):
     from oracle import ref_model
-    from tensor_op_cases import CASES, INT_CASES, make_inputs
+    from tensor_op_cases import CASES, INT_CASES, MULTI_CASES, make_inputs
     soket = ref_model.import_reference()
 
     def to_numpy(t):
@@ -44,6 +44,17 @@ def run_case(index, out_path):
         view[tuple(slice(None) for _ in t.shape)] = t
         return buf
     cases = CASES + INT_CASES
+    if index >= len(cases):               # dtype / creation tables: a list of results per case
+        name, fn = MULTI_CASES[index - len(cases)]
+        res = {}
+        for i, o in enumerate(fn(soket, None)):
+            if isinstance(o, str):
+                res[f"r{i:02d}"] = np.array(o)
+            else:
+                res[f"r{i:02d}"] = to_numpy(o)
+                res[f"r{i:02d}_dtype"] = np.array(str(o.dtype))      # the Tensor's dtype TAG
+        np.savez(out_path, **res)
+        return
     name, shapes, fn = cases[index]
     xs = [soket.Tensor(a, requires_grad=True) for a in make_inputs(shapes, seed_of(name))]
     out = fn(soket, *xs)
@@ -63,8 +74,8 @@ def run_case(index, out_path):
 
 
 def main():
-    from tensor_op_cases import CASES, INT_CASES
-    cases = CASES + INT_CASES
+    from tensor_op_cases import CASES, INT_CASES, MULTI_CASES
+    cases = CASES + INT_CASES + [(n, None, f) for n, f in MULTI_CASES]
     golden, crashes = {}, []
     with tempfile.TemporaryDirectory() as tmp:
         for i, (name, _, _) in enumerate(cases):

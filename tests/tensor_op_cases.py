@@ -102,3 +102,76 @@ INT_CASES = [
 def make_inputs(shapes, seed):
     rng = np.random.default_rng(seed)
     return [rng.standard_normal(shp).astype("float32") for shp in shapes]
+
+
+# ---- dtype semantics: promotion table (soket/dtype.pyx), scalar typing (dtype.pyx:157-167), casts,
+# creation functions (soket/tensor/creation.pyx).  Forward only; the result's dtype TAG and values are
+# compared exactly (values within 1e-5 for float results).
+def _ints(shape, dtype, seed):
+    return np.random.default_rng(seed).integers(1, 9, shape).astype(dtype)
+
+
+def _try(thunk):
+    """The result, or the exception type when the expression is rejected (e.g. the reference's
+    true-divide on integer result dtypes: numpy has no such loop -> TypeError)."""
+    try:
+        return thunk()
+    except Exception as e:
+        return "raises " + type(e).__name__
+
+
+def _mixed(op):
+    def run(s, a):
+        out = []
+        pairs = [("int32", "float32"), ("uint8", "int32"), ("int64", "float32"), ("uint8", "float64"),
+                 ("int8", "uint8"), ("int64", "uint64"), ("float16", "float32"), ("int32", "int64"),
+                 ("bool", "int32"), ("bool", "float32"), ("float32", "float64"), ("uint16", "int16")]
+        for i, (da, db) in enumerate(pairs):
+            x = _t(s, _ints((2, 3), da, i) if da != "bool" else (_ints((2, 3), "int8", i) > 4))
+            y = _t(s, _ints((2, 3), db, 100 + i) if db != "bool" else (_ints((2, 3), "int8", 100 + i) > 4))
+            out.append(_try(lambda: op(x, y)))
+        return out
+    return run
+
+
+def _scalars(s, a):
+    out = []
+    for i, dt in enumerate(["int32", "uint8", "int64", "float32", "float64", "float16", "bool"]):
+        x = _t(s, _ints((2, 3), dt, i) if dt != "bool" else (_ints((2, 3), "int8", i) > 4))
+        out += [_try(f) for f in (lambda: x + 2, lambda: x * 2.5, lambda: x - True, lambda: 3 - x, lambda: x / 2,
+                                  lambda: 2.0 / (x + 1), lambda: x ** 2, lambda: x * -1)]
+    return out
+
+
+def _casts(s, a):
+    base = _t(s, (np.arange(12, dtype="float32").reshape(3, 4) - 4.5) * 1.5)
+    out = []
+    for name in ["float16", "float32", "float64", "int8", "uint8", "int16", "int32", "int64", "bool"]:
+        out.append(s.Tensor(base, dtype=getattr(s, name)))
+    ints = _t(s, np.arange(-3, 9, dtype="int32").reshape(3, 4))
+    out += [s.Tensor(ints, dtype=s.float32), s.Tensor(ints, dtype=s.uint8), s.Tensor(ints, dtype=s.bool),
+            s.Tensor([1, 2, 3]), s.Tensor([1.5, 2.5]), s.Tensor(7), s.Tensor(2.5), s.Tensor(True),
+            s.Tensor([[1, 2], [3, 4]], dtype=s.float64), base.copy(), base.detach(), ints.sum(), ints.mean(),
+            ints.max(), (ints > 2).sum(), (ints > 2).mean(dtype=s.float32), ints.sum(0, dtype=s.float32)]
+    return out
+
+
+def _creation(s, a):
+    like = _t(s, np.zeros((2, 5), "int32"))
+    return [s.zeros(2, 3), s.ones(4), s.zeros((2, 2), dtype=s.int32), s.ones(2, 2, dtype=s.float64),
+            s.full(2, 3, fill=2.5), s.full((3,), fill=7, dtype=s.int64), s.zeros_like(like), s.one_like(like),
+            s.zeros_like(like, dtype=s.float32), s.empty(2, 3) * 0.0,
+            s.rand(3, 4) * 0.0, s.randn(2, 2, dtype=s.float64) * 0.0, s.randb(5, p=1.0), s.randb(2, 3, p=0.0)]
+
+
+MULTI_CASES = [
+    ("mixed_add", _mixed(lambda x, y: x + y)),
+    ("mixed_sub", _mixed(lambda x, y: x - y)),
+    ("mixed_mul", _mixed(lambda x, y: x * y)),
+    ("mixed_div", _mixed(lambda x, y: x / y)),
+    ("mixed_eq", _mixed(lambda x, y: x == y)),
+    ("mixed_gt", _mixed(lambda x, y: x > y)),
+    ("scalar_operands", _scalars),
+    ("casts_and_constructors", _casts),
+    ("creation_functions", _creation),
+]

@@ -93,3 +93,33 @@ def test_integer_and_bool_results_exact(sk, case):
     out = fn(soket, *xs)
     assert not out.requires_grad
     close(out.numpy(), GOLD[f"{name}/out"], name)
+
+
+from tensor_op_cases import MULTI_CASES  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", MULTI_CASES, ids=[c[0] for c in MULTI_CASES])
+def test_dtype_semantics_and_creation_match_reference(sk, case):
+    """Promotion table, Python-scalar typing, casts / constructors and the creation functions:
+    the result's dtype TAG, shape and values (and the exception type where the reference rejects
+    the expression, e.g. true-divide producing an integer dtype) equal the reference's."""
+    import soket_b200.api as soket
+    name, fn = case
+    outs = fn(soket, None)
+    keys = sorted(k for k in GOLD.files if k.startswith(name + "/r") and not k.endswith("_dtype"))
+    assert len(outs) == len(keys), (len(outs), len(keys))
+    for i, (o, key) in enumerate(zip(outs, keys)):
+        want = GOLD[key]
+        if want.dtype.kind in "US":
+            assert isinstance(o, str) and o == str(want), (name, i, o, str(want))
+            continue
+        assert not isinstance(o, str), (name, i, o)
+        assert str(o.dtype) == str(GOLD[key + "_dtype"]), (name, i, str(o.dtype), str(GOLD[key + "_dtype"]))
+        got = o.numpy()
+        assert got.shape == want.shape, (name, i, got.shape, want.shape)
+        got = got.astype(want.dtype)
+        if want.dtype.kind in "biu":
+            assert np.array_equal(got, want), (name, i, got, want)
+        else:
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-7, equal_nan=True), (name, i, got, want)
