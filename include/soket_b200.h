@@ -262,6 +262,19 @@ int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const
                      const float *mean, const float *rstd, const float *y_out, int mask_mode,
                      float *dx, float *dgamma, float *dbeta, float *dresidual,
                      int64_t rows, int64_t cols);
+/* LayerNorm (+ReLU) followed by Dropout in ONE pass each way (the Linear - LayerNorm - ReLU -
+ * Dropout run of the residual block, model.py:24-31; prototypes.pyx:746-760 for the dropout):
+ * y = (relu(LN(x)) * mask) * (1/keep), mask ~ Bernoulli(keep) identified by *seed (the same draw
+ * sk_dropout_fwd_seeded would make); the backward takes the adjoint of y, regenerates the mask
+ * from seed ((adj * r_keep) * mask), recomputes the ReLU mask and runs the LayerNorm backward.
+ * Bit-identical to sk_layernorm_fwd + sk_dropout_fwd_seeded / sk_dropout_bwd + sk_layernorm_bwd. */
+int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y,
+                             float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                             int relu, float keep, uint64_t *seed);
+int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                             const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                             uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                             int64_t cols);
 /* BatchNorm1d over axis 0 of a contiguous (rows, cols) fp32 matrix, training
  * mode (always: quirk Q4, forward.pyx:281), biased variance, running stats
  * rm = (1-m) rm + m mean (forward.pyx:308-318). */

@@ -157,6 +157,13 @@ cdef extern from "soket_b200.h" nogil:
     int sk_add_relu(const float *a, const float *b, float *out, int64_t n)
     int sk_dropout_fwd(const float *x, float *out, float *mask, int64_t n, float keep)
     int sk_dropout_fwd_seeded(const float *x, float *out, int64_t n, float keep, uint64_t *seed)
+    int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y,
+                                 float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                                 int relu, float keep, uint64_t *seed)
+    int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                                 const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                                 uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                                 int64_t cols)
     int sk_dropout_bwd(const float *adj, float *out, int64_t n, float keep, float r_keep, uint64_t seed)
     int sk_colsum(const float *adj, const float *y_out, float *out, int64_t rows, int64_t cols)
     int sk_accumulate(float *acc, const float *part, int64_t n)

@@ -62,6 +62,35 @@ def layernorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rst
     return dx, dg, db, dres
 
 
+def layernorm_dropout_fwd(ndarray x, gamma, beta, double eps, bint relu, double keep):
+    """y = dropout([relu](LN(x))) in one pass.  Returns (y, mean, rstd, seed)."""
+    cdef int64_t rows, cols
+    _rows_cols(x, &rows, &cols)
+    cdef ndarray y = _new_array(x._ndim, x._shape, SK_F32)
+    cdef ndarray mean = _new_array(1, &rows, SK_F32)
+    cdef ndarray rstd = _new_array(1, &rows, SK_F32)
+    cdef uint64_t seed = 0
+    _check(sk_layernorm_dropout_fwd(_fptr(x), _opt(gamma), _opt(beta), _fptr(y), _fptr(mean), _fptr(rstd),
+                                    rows, cols, <float> eps, relu, <float> keep, &seed))
+    return y, mean, rstd, seed
+
+
+def layernorm_dropout_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd, bint relu,
+                          double keep, double r_keep, seed, bint want_params=True):
+    """Backward of layernorm_dropout_fwd from the adjoint of its output.  Returns (dx, dgamma, dbeta)."""
+    cdef int64_t rows, cols
+    _rows_cols(x, &rows, &cols)
+    cdef ndarray dx = _new_array(x._ndim, x._shape, SK_F32)
+    cdef ndarray dg = None, db = None
+    if want_params:
+        dg = _new_array(1, &cols, SK_F32)
+        db = _new_array(1, &cols, SK_F32)
+    _check(sk_layernorm_dropout_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
+                                    relu, <float> keep, <float> r_keep, <uint64_t> seed, _fptr(dx),
+                                    _opt(dg), _opt(db), rows, cols))
+    return dx, dg, db
+
+
 def batchnorm_fwd(ndarray x, gamma=None, beta=None, running_mean=None, running_var=None,
                   double eps=1e-5, double momentum=0.1, bint relu=False):
     """Training-mode BatchNorm1d over axis 0 of (rows, cols); running stats updated in

@@ -53,6 +53,7 @@ void note_launch();
 inline cudaStream_t stream() { return ctx().stream; }
 // device-resident counter mixed into dropout seeds at RUN time; a captured graph advances it per replay
 const uint64_t *rng_epoch_ptr();
+void dropout_reseed(uint64_t seed);   // nn_fused.cu: sk_rng_seed also restarts the dropout draw sequence
 
 // ---- per-family profiling (sk_prof_*) -------------------------------------------
 // Usage inside a launcher:  ProfScope ps(SK_PROF_GEMM_TC, flops);  ... launch ...

@@ -37,6 +37,54 @@ __device__ __forceinline__ float group_sum(float v, float *smem) {
   return t;
 }
 
+// Philox is private to rng.cu; dropout uses a cheap counter hash (PCG-style
+// output permutation over a Weyl sequence keyed by seed): one draw per element.
+__device__ __forceinline__ uint32_t hash_u32(uint64_t idx, uint64_t seed) {
+  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+
+// Dropout folded into the LayerNorm kernels (Linear - LayerNorm - ReLU - Dropout of the residual
+// block, model.py:24-31): the same per-element Bernoulli draw as dropout_kernel / dropout_bwd_kernel
+// (element index = row * C + column, seed mixed with the graph-replay epoch), applied to the
+// LayerNorm(+ReLU) OUTPUT in the forward epilogue and to the incoming adjoint in the backward
+// prologue.  keep >= 1 switches it off.
+struct DropSpec {
+  float keep, r_keep;
+  uint64_t seed;
+  const uint64_t *epoch;
+};
+__device__ __forceinline__ uint64_t drop_seed(const DropSpec &d) {
+  return d.keep < 1.f ? d.seed + *d.epoch * 0xD1B54A32D192ED03ull : 0ull;
+}
+// ONE 64-bit hash per aligned group of four elements, 16 bits per element: the hash (three 64-bit
+// multiplies) was the visible cost once the draw moved into the LayerNorm kernels.  P(keep) is
+// floor(keep * 65536) / 65536, within 1.6e-5 of `keep`.  e0 is a multiple of 4.
+__device__ __forceinline__ float4 drop_mask4(int64_t e0, uint64_t seed, float keep) {
+  uint64_t z = ((uint64_t)e0 >> 2) * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const uint32_t thr = (uint32_t)(keep * 65536.0f);
+  const uint32_t lo = (uint32_t)z, hi = (uint32_t)(z >> 32);
+  float4 m;
+  m.x = (lo & 0xFFFFu) < thr ? 1.f : 0.f;
+  m.y = (lo >> 16) < thr ? 1.f : 0.f;
+  m.z = (hi & 0xFFFFu) < thr ? 1.f : 0.f;
+  m.w = (hi >> 16) < thr ? 1.f : 0.f;
+  return m;
+}
+// forward: (y * mask) * (1/keep) (prototypes.pyx:758); backward: (adj * (1/keep)) * mask
+__device__ __forceinline__ void drop_fwd4(float4 &o, const float4 &m, float r_keep) {
+  o.x = (o.x * m.x) * r_keep; o.y = (o.y * m.y) * r_keep; o.z = (o.z * m.z) * r_keep; o.w = (o.w * m.w) * r_keep;
+}
+__device__ __forceinline__ void drop_bwd4(float4 &a, const float4 &m, float r_keep) {
+  a.x = (a.x * r_keep) * m.x; a.y = (a.y * r_keep) * m.y; a.z = (a.z * r_keep) * m.z; a.w = (a.w * r_keep) * m.w;
+}
+
 __device__ __forceinline__ float affine(float xs, float r, float g, float b) {
   // gamma * (xs * r) + beta, in the reference's order (forward.pyx:325,343,352)
   return __fadd_rn(__fmul_rn(g, __fmul_rn(xs, r)), b);
@@ -50,8 +98,9 @@ __global__ void __launch_bounds__(kNT)
 ln_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
               const float *__restrict__ beta, const float *__restrict__ residual,
               float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-              int64_t R, int C, float eps, int relu) {
+              int64_t R, int C, float eps, int relu, const DropSpec drop) {
   __shared__ float smem[kNT / 32];
+  const uint64_t dseed = drop_seed(drop);
   constexpr int RPB = kNT / TPR;  // rows per block
   const int t = threadIdx.x % TPR;
   const int C4 = C >> 2;
@@ -105,6 +154,7 @@ ln_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
           o.z = __fadd_rn(rs.z, o.z); o.w = __fadd_rn(rs.w, o.w);
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (drop.keep < 1.f) drop_fwd4(o, drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         st_stream(yr + i, o);
       }
     }
@@ -122,8 +172,9 @@ ln_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ x,
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
               const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
               float *__restrict__ dresidual, float *__restrict__ part_g,
-              float *__restrict__ part_b, int64_t R, int C) {
+              float *__restrict__ part_b, int64_t R, int C, const DropSpec drop) {
   __shared__ float smem[kNT / 32];
+  const uint64_t dseed = drop_seed(drop);
   constexpr int RPB = kNT / TPR;
   const int t = threadIdx.x % TPR;
   const int grp = threadIdx.x / TPR;
@@ -148,6 +199,7 @@ ln_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ x,
       int i = t + j * TPR;
       if (live && i < C4) {
         a[j] = ld_stream(ar + i);
+        if (drop.keep < 1.f) drop_bwd4(a[j], drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         xs[j] = ld_stream(xr + i);
         xs[j].x -= mean; xs[j].y -= mean; xs[j].z -= mean; xs[j].w -= mean;
         float4 g = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -274,8 +326,10 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
                      const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
                      const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
                      float *__restrict__ dresidual, float *__restrict__ part_g,
-                     float *__restrict__ part_b, int64_t R, int C, int stages, int *__restrict__ sched) {
+                     float *__restrict__ part_b, int64_t R, int C, int stages, int *__restrict__ sched,
+                     const DropSpec drop) {
   extern __shared__ __align__(128) uint8_t ln_sm[];
+  const uint64_t dseed = drop_seed(drop);
   float *red = reinterpret_cast<float *>(ln_sm);
   uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
   volatile int *row_ring = reinterpret_cast<volatile int *>(ln_sm + 224);   // [kLnMaxStages] claimed rows
@@ -341,6 +395,7 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
       const int i = t + j * kNT;
       if (i < C4) {
         a[j] = ar[i];
+        if (drop.keep < 1.f) drop_bwd4(a[j], drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         xs[j] = xr[i];
         xs[j].x -= mean; xs[j].y -= mean; xs[j].z -= mean; xs[j].w -= mean;
         float4 g = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -417,8 +472,9 @@ __global__ void __launch_bounds__(kNT, 2)
 ln_fwd_staged_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                      const float *__restrict__ beta, const float *__restrict__ residual,
                      float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-                     int64_t R, int C, float eps, int relu, int stages) {
+                     int64_t R, int C, float eps, int relu, int stages, const DropSpec drop) {
   extern __shared__ __align__(128) uint8_t ln_sm[];
+  const uint64_t dseed = drop_seed(drop);
   float *red = reinterpret_cast<float *>(ln_sm);
   uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
   float *data = reinterpret_cast<float *>(ln_sm + kLnHeader);
@@ -499,6 +555,7 @@ ln_fwd_staged_kernel(const float *__restrict__ x, const float *__restrict__ gamm
           o.z = __fadd_rn(rs[j].z, o.z); o.w = __fadd_rn(rs[j].w, o.w);
         }
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (drop.keep < 1.f) drop_fwd4(o, drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         st_stream(yr + i, o);
       }
     }
@@ -562,7 +619,8 @@ ln_param_grads_kernel(const float *__restrict__ part_g, const float *__restrict_
 
 template <int TPR, int VPT>
 static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, const float *residual,
-                         float *y, float *mean, float *rstd, int64_t R, int C, float eps, int relu) {
+                         float *y, float *mean, float *rstd, int64_t R, int C, float eps, int relu,
+                         const DropSpec drop) {
   constexpr int RPB = kNT / TPR;
   if (TPR == kNT) {
     int stages, bps = 1;
@@ -578,14 +636,14 @@ static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, 
       const int64_t cap = (int64_t)ctx().num_sms * bps;
       const int grid = (int)(R < cap ? R : cap);
       ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
-      kern<<<grid, kNT, smem, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, stages);
+      kern<<<grid, kNT, smem, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, stages, drop);
       SK_LAUNCH_CHECK();
       return SK_OK;
     }
   }
   int grid = grid_for(R, RPB, 8);
   ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
-  ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu);
+  ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, drop);
   SK_LAUNCH_CHECK();
   return SK_OK;
 }
@@ -593,7 +651,8 @@ static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, 
 template <int TPR, int VPT>
 static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, const float *beta,
                          const float *mean, const float *rstd, const float *y_out, int mask_mode,
-                         float *dx, float *dresidual, float *dgamma, float *dbeta, int64_t R, int C) {
+                         float *dx, float *dresidual, float *dgamma, float *dbeta, int64_t R, int C,
+                         const DropSpec drop) {
   constexpr int RPB = kNT / TPR;
   // persistent: each group walks many rows so the dgamma/dbeta partial matrix stays small
   int64_t need = (R + RPB - 1) / RPB;
@@ -625,10 +684,10 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
         SK_CUDA(cudaMemsetAsync(sched_dev, 0, 2 * sizeof(int), stream()));
       }
       kern<<<grid, kNT, smem, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, part,
-                                          part ? part + P * C : nullptr, R, C, stages, sched_dev);
+                                          part ? part + P * C : nullptr, R, C, stages, sched_dev, drop);
     } else {
       ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
-                                                         dresidual, part, part ? part + P * C : nullptr, R, C);
+                                                         dresidual, part, part ? part + P * C : nullptr, R, C, drop);
     }
   }
   SK_LAUNCH_CHECK();
@@ -963,15 +1022,6 @@ accumulate_kernel(float *__restrict__ acc, const float *__restrict__ part, int64
   }
 }
 
-// Philox is private to rng.cu; dropout uses a cheap counter hash (PCG-style
-// output permutation over a Weyl sequence keyed by seed): one draw per element.
-__device__ __forceinline__ uint32_t hash_u32(uint64_t idx, uint64_t seed) {
-  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
-}
 __global__ void __launch_bounds__(kNT)
 dropout_kernel(const float *__restrict__ x, float *__restrict__ out, float *__restrict__ mask,
                int64_t n, float keep, float r_keep, uint64_t seed, const uint64_t *__restrict__ epoch) {
@@ -980,11 +1030,7 @@ dropout_kernel(const float *__restrict__ x, float *__restrict__ out, float *__re
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * kNT + threadIdx.x; i < n4; i += stride) {
     float4 v = ld_stream(reinterpret_cast<const float4 *>(x) + i);
-    float4 m;
-    m.x = (float)(hash_u32(4 * i + 0, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.y = (float)(hash_u32(4 * i + 1, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.z = (float)(hash_u32(4 * i + 2, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.w = (float)(hash_u32(4 * i + 3, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    const float4 m = drop_mask4(4 * i, seed, keep);
     float4 o;  // (x * mask) * (1/keep): prototypes.pyx:758
     o.x = (v.x * m.x) * r_keep; o.y = (v.y * m.y) * r_keep; o.z = (v.z * m.z) * r_keep; o.w = (v.w * m.w) * r_keep;
     st_stream(reinterpret_cast<float4 *>(out) + i, o);
@@ -1009,11 +1055,7 @@ dropout_bwd_kernel(const float *__restrict__ adj, float *__restrict__ out, int64
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * kNT + threadIdx.x; i < n4; i += stride) {
     const float4 a = ld_stream(reinterpret_cast<const float4 *>(adj) + i);
-    float4 m;
-    m.x = (float)(hash_u32(4 * i + 0, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.y = (float)(hash_u32(4 * i + 1, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.z = (float)(hash_u32(4 * i + 2, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
-    m.w = (float)(hash_u32(4 * i + 3, seed) >> 8) * (1.0f / 16777216.0f) < keep ? 1.f : 0.f;
+    const float4 m = drop_mask4(4 * i, seed, keep);
     float4 o;
     o.x = (a.x * r_keep) * m.x; o.y = (a.y * r_keep) * m.y; o.z = (a.z * r_keep) * m.z; o.w = (a.w * r_keep) * m.w;
     st_stream(reinterpret_cast<float4 *>(out) + i, o);
@@ -1056,6 +1098,13 @@ colsum_mask_kernel(const float *__restrict__ adj, const float *__restrict__ y_ou
 
 static uint64_t g_dropout_seed = 0x0d15ea5e;
 static uint64_t g_dropout_calls = 0;
+void dropout_reseed(uint64_t seed) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull;            // splitmix64 of the user seed
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  g_dropout_seed = z ^ (z >> 31);
+  g_dropout_calls = 0;
+}
 
 
 }  // namespace sk
@@ -1076,7 +1125,28 @@ int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta, cons
                  (!residual || al16(residual)),
              "sk_layernorm_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return SK_OK;
-  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, residual, y, mean, rstd, rows, (int)cols, eps, relu);
+  const DropSpec off = {1.f, 1.f, 0ull, nullptr};
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, residual, y, mean, rstd, rows, (int)cols, eps, relu, off);
+  return SK_ERR_UNSUPPORTED;
+}
+
+int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                             float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
+                             uint64_t *seed_out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(x && y && mean && rstd && seed_out, "sk_layernorm_dropout_fwd: null pointer");
+  SK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 8192,
+             "sk_layernorm_dropout_fwd: cols must be a multiple of 4 and <= 8192 (got %lld)", (long long)cols);
+  SK_REQUIRE(keep > 0.f && keep < 1.f, "sk_layernorm_dropout_fwd: keep rate must be in (0, 1)");
+  SK_REQUIRE(al16(x) && al16(y) && (!gamma || al16(gamma)) && (!beta || al16(beta)),
+             "sk_layernorm_dropout_fwd: pointers must be 16-byte aligned");
+  // one draw per call from the same sequence as sk_dropout_fwd_seeded
+  const uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
+  *seed_out = seed;
+  if (rows == 0) return SK_OK;
+  const DropSpec drop = {keep, (float)(1.0 / (double)keep), seed, rng_epoch_ptr()};
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, nullptr, y, mean, rstd, rows, (int)cols, eps, relu, drop);
   return SK_ERR_UNSUPPORTED;
 }
 
@@ -1093,8 +1163,27 @@ int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const
   SK_REQUIRE(mask_mode != 2 || y_out, "sk_layernorm_bwd: mask_mode 2 needs y_out");
   SK_REQUIRE(al16(adj) && al16(x) && al16(dx), "sk_layernorm_bwd: pointers must be 16-byte aligned");
   if (rows == 0) return SK_OK;
+  const DropSpec off = {1.f, 1.f, 0ull, nullptr};
   LN_DISPATCH(ln_bwd_launch, adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, dgamma,
-              dbeta, rows, (int)cols);
+              dbeta, rows, (int)cols, off);
+  return SK_ERR_UNSUPPORTED;
+}
+
+int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                             const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                             uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                             int64_t cols) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(adj && x && mean && rstd && dx, "sk_layernorm_dropout_bwd: null pointer");
+  SK_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 8192,
+             "sk_layernorm_dropout_bwd: cols must be a multiple of 4 and <= 8192 (got %lld)", (long long)cols);
+  SK_REQUIRE(keep > 0.f && keep < 1.f, "sk_layernorm_dropout_bwd: keep rate must be in (0, 1)");
+  SK_REQUIRE(al16(adj) && al16(x) && al16(dx), "sk_layernorm_dropout_bwd: pointers must be 16-byte aligned");
+  if (rows == 0) return SK_OK;
+  const DropSpec drop = {keep, r_keep, seed, rng_epoch_ptr()};
+  LN_DISPATCH(ln_bwd_launch, adj, x, gamma, beta, mean, rstd, nullptr, relu ? 1 : 0, dx, nullptr, dgamma,
+              dbeta, rows, (int)cols, drop);
   return SK_ERR_UNSUPPORTED;
 }
 

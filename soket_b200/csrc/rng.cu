@@ -104,6 +104,7 @@ extern "C" {
 int sk_rng_seed(uint64_t seed) {
   g_seed = seed;
   g_offset = 0;
+  dropout_reseed(seed);   // Dropout masks follow the seed too (per-rank seeds => per-rank masks)
   return SK_OK;
 }
 int sk_rng_uniform(sk_array *out, double low, double high) {

@@ -1131,16 +1131,33 @@ def linear(Tensor x, Tensor w, b=None, bint relu=False):
     return Tensor._from_op(_LinearOp(relu), (x, w, b), y, x._dtype)
 
 
+import os as _os
+_FUSE_DROPOUT = _os.environ.get('SOKET_B200_FUSE_DROPOUT', '1') != '0'
+
+
+def set_dropout_fusion(on):
+    global _FUSE_DROPOUT
+    _FUSE_DROPOUT = bool(on)
+
+
 class _LayerNormOp(Op):
     """Fused LayerNorm (+ residual add) (+ ReLU): functional.pyx:82-144 +
     forward.pyx:274-353 in one pass; backward.pyx:1025-1132 in one pass."""
     name = 'layer_norm'
-    def __init__(self, mean, rstd, relu, has_residual):
+    def __init__(self, mean, rstd, relu, has_residual, drop=None):
         self.mean = mean; self.rstd = rstd; self.relu = relu; self.has_residual = has_residual
+        self.drop = drop      # (keep, seed): the output went through a fused Dropout
     def bwd(self, node, adj):
         g, b, x, res = node._inputs
         if not adj.is_contiguous:
             adj = B.ascontiguousarray(adj)
+        if self.drop is not None:
+            keep, seed = self.drop
+            want_p = (g is not None and g.requires_grad) or (b is not None and b.requires_grad)
+            dx, dg, db = F.layernorm_dropout_bwd(
+                adj, x._data, None if g is None else g._data, None if b is None else b._data,
+                self.mean, self.rstd, self.relu, keep, 1.0 / keep, seed, want_p)
+            return (dg, db, dx if x.requires_grad else None, None)
         mode = 0
         if self.relu:
             mode = 2 if self.has_residual else 1
@@ -1153,6 +1170,27 @@ class _LayerNormOp(Op):
         if want_res and mode != 2:
             dres = adj    # plain residual add: the adjoint passes through (aliased)
         return (dg, db, dx if x.requires_grad else None, dres if want_res else None)
+
+
+def layer_norm_dropout(Tensor X, weight, bias, eps, bint relu, keep_rate):
+    """dropout([relu](layer_norm(X))) -- the LayerNorm - ReLU - Dropout run of the residual block
+    (model.py:24-31) as ONE kernel each way when the fused LayerNorm takes the shape, else the two
+    ops in sequence.  SOKET_B200_FUSE_DROPOUT=0 keeps them apart."""
+    cdef ndarray xd = X._data
+    ok = (_FUSE_DROPOUT and xd.ndim == 2 and X._dtype.name == 'float32' and xd.shape[1] % 4 == 0
+          and xd.shape[1] <= 8192 and 0.0 < keep_rate < 1.0)
+    for p in (weight, bias):
+        if p is not None and ((<Tensor> p)._dtype != X._dtype or (<Tensor> p)._data.size != xd.shape[1]):
+            ok = False
+    if not ok:
+        return dropout(layer_norm(X, weight, bias, eps, relu, None), keep_rate)
+    if not xd.is_contiguous:
+        xd = B.ascontiguousarray(xd)
+    y, mean, rstd, seed = F.layernorm_dropout_fwd(
+        xd, None if weight is None else (<Tensor> weight)._data.reshape(-1),
+        None if bias is None else (<Tensor> bias)._data.reshape(-1), eps, relu, keep_rate)
+    op = _LayerNormOp(mean, rstd, relu, False, (keep_rate, seed))
+    return Tensor._from_op(op, (weight, bias, X, None), y, X._dtype)
 
 
 def layer_norm(Tensor X, weight=None, bias=None, eps=1e-5, bint relu=False, residual=None):

@@ -9,6 +9,7 @@ as the reference; what changes is what one forward call launches:
   Linear -> ReLU      matmul + add + maximum       -> 1 GEMM with bias+ReLU epilogue
   LayerNorm           9 array calls                -> 1 kernel (x read once)
   LayerNorm -> ReLU   10                           -> same kernel, ReLU epilogue
+  LN -> ReLU -> Dropout  10 + binomial+astype+2 mul -> same kernel, dropout in the epilogue (backward: in the prologue)
   Residual -> ReLU    add + maximum (+ LN's 9)     -> relu(x + LN(.)) in LN's epilogue
   BatchNorm1d         17 array calls               -> 3 kernels (stats, finalise, apply)
   Dropout             binomial+astype+2 mul        -> 1 kernel
@@ -393,6 +394,13 @@ cdef class Sequential(Module):
             m = <Module> self._storage[i]
             nxt = self._storage[i + 1] if i + 1 < stop else None
             if _FUSE and type(nxt) is ReLU and m._builtin:
+                if type(m) is LayerNorm and i + 2 < stop and type(self._storage[i + 2]) is Dropout:
+                    # LayerNorm - ReLU - Dropout (model.py:24-31): one kernel
+                    drop = <Dropout> self._storage[i + 2]
+                    if drop._training and drop._keep_rate < 1.0:
+                        ln = <LayerNorm> m
+                        Y = E.layer_norm_dropout(Y, ln._storage[0], ln._storage[1], ln._eps, True, drop._keep_rate)
+                        i += 3; continue
                 if type(m) is Linear:
                     Y = (<Linear> m)._forward(Y, True); i += 2; continue
                 if type(m) is LayerNorm:

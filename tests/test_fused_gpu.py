@@ -176,3 +176,69 @@ def test_adam_bit_exact(sk, F, wd):
         F.adam_step(dP, [sk.array(g) for g in G], dM, dV, 0.001, 0.9, 0.999, 1e-8, wd, omb1_t, omb2_t, step == 0, 1.0)
         for i, (p, d) in enumerate(zip(P, dP)):
             assert np.array_equal(sk.asnumpy(d), p), (step, i)
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 4096), (37, 256), (5, 1024), (300, 100)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_layernorm_dropout_fused_equals_the_two_kernels(sk, F, rows, cols, relu):
+    """sk_layernorm_dropout_fwd / _bwd (LayerNorm - ReLU - Dropout in one pass each way) against
+    sk_layernorm_fwd + the seeded dropout kernels + sk_layernorm_bwd on the same draw: identical
+    values (staged and register LayerNorm kernels; -0.0 == 0.0)."""
+    rng = np.random.default_rng(rows * cols + relu)
+    x = sk.array(rng.standard_normal((rows, cols)).astype("float32"))
+    g = sk.array((1 + 0.1 * rng.standard_normal(cols)).astype("float32"))
+    b = sk.array((0.1 * rng.standard_normal(cols)).astype("float32"))
+    adj = sk.array(rng.standard_normal((rows, cols)).astype("float32"))
+    keep = 0.7
+    y, mean, rstd, seed = F.layernorm_dropout_fwd(x, g, b, 1e-5, relu, keep)
+    y0, mean0, rstd0 = F.layernorm_fwd(x, g, b, None, 1e-5, relu)
+    r_fwd = float(np.float32(1.0 / np.float64(np.float32(keep))))       # what the forward kernels use
+    want_y = sk.asnumpy(F.dropout_bwd(y0, keep, r_fwd, seed))           # (y * r) * m == (y * m) * r
+    got_y = sk.asnumpy(y)
+    assert np.array_equal(got_y, want_y)
+    frac = float((got_y == 0).mean())
+    assert (0.55 if relu else 0.25) < frac < (0.75 if relu else 0.35)  # ~30 % dropped (+ ~50 % by the ReLU)
+    assert np.array_equal(sk.asnumpy(mean), sk.asnumpy(mean0)) and np.array_equal(sk.asnumpy(rstd), sk.asnumpy(rstd0))
+    r_bwd = 1.0 / keep
+    dx, dg, db = F.layernorm_dropout_bwd(adj, x, g, b, mean, rstd, relu, keep, r_bwd, seed)
+    adj0 = F.dropout_bwd(adj, keep, r_bwd, seed)
+    dx0, dg0, db0, _ = F.layernorm_bwd(adj0, x, g, b, mean0, rstd0, None, 1 if relu else 0)
+    assert np.array_equal(sk.asnumpy(dx), sk.asnumpy(dx0))
+    assert np.array_equal(sk.asnumpy(dg), sk.asnumpy(dg0)) and np.array_equal(sk.asnumpy(db), sk.asnumpy(db0))
+
+
+def test_sequential_fuses_layernorm_relu_dropout(sk):
+    """nn.Sequential(Linear, LayerNorm, ReLU, Dropout, Linear) under the same seed: the fused
+    LayerNorm-ReLU-Dropout kernel and the separate kernels give identical outputs and gradients,
+    with one launch less each way."""
+    import soket_b200.api as soket
+    from soket_b200 import engine as E, nn
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((64, 32)).astype("float32")
+    W = [rng.standard_normal(s).astype("float32") * 0.3 for s in ((32, 64), (64,), (64,), (64,), (64, 8), (8,))]
+    results = []
+    try:
+        for fuse in (True, False):
+            E.set_dropout_fusion(fuse)
+            m = nn.Sequential(nn.Linear(32, 64), nn.LayerNorm(64), nn.ReLU(), nn.Dropout(p=0.4), nn.Linear(64, 8))
+            for p, w in zip(m.parameters(), W):
+                p.data = soket.Tensor(w.copy())
+            m.train(True)
+            sk.random.seed(77)
+            x = soket.Tensor(X, requires_grad=True)
+            n0 = sk.launch_count()
+            out = m(x)
+            n1 = sk.launch_count()
+            out.sum().backward()
+            results.append((out.numpy(), x.grad.numpy(), [p.grad.numpy() for p in m.parameters()], n1 - n0))
+    finally:
+        E.set_dropout_fusion(True)
+    (o1, g1, p1, l1), (o2, g2, p2, l2) = results
+    assert np.array_equal(o1, o2) and np.array_equal(g1, g2)
+    for a, c in zip(p1, p2):
+        assert np.array_equal(a, c)
+    assert l1 == l2 - 1
+    assert 0.3 < float((o1 == o2).mean()) and float(np.abs(o1).sum()) > 0
+    sk.random.seed(78)                                     # another seed, another mask
+    m.train(True)
+    assert not np.array_equal(m(soket.Tensor(X)).numpy(), o2)
