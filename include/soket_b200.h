@@ -240,6 +240,10 @@ int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
  * dw (I,O) = x(B,I).T @ adj in one call, so that the fp16x3 path splits adj once for both
  * GEMMs; falls back to two sk_matmul calls on .T views for other shapes / layouts. */
 int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw);
+/* the same plus the bias gradient db[o] = sum_b adj[b, o] (autodiff.pyx:84-90; contiguous float32
+ * vector of O elements): on the fp16x3 path it is a by-product of the pass that splits adj. */
+int sk_linear_bwd_bias(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx,
+                       sk_array *dw, float *db);
 /* fp32 -> bf16 (RNE) cast for the bf16 sweep */
 int sk_cast_bf16(const sk_array *src, sk_array *dst);
 

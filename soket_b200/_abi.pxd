@@ -136,6 +136,7 @@ cdef extern from "soket_b200.h" nogil:
                       sk_array *out, int epilogue, int algo)
     int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw)
     int sk_cast_bf16(const sk_array *src, sk_array *dst)
+    int sk_linear_bwd_bias(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw, float *db)
 
     int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta,
                          const float *residual, float *y, float *mean, float *rstd,

@@ -1285,9 +1285,10 @@ def linear(x, w, bias=None, relu=False, algo=None):
     return _matmul_impl(x, w, bias, epi, _DEFAULT_MM_ALGO if algo is None else <int> algo)
 
 
-def linear_bwd(adj, x, w):
+def linear_bwd(adj, x, w, bint want_bias=False):
     """Backward of y = x @ w (backward.pyx:704-742): returns (adj @ w.T, x.T @ adj) from one
-    call, so that the fp16x3 path splits `adj` once for both GEMMs."""
+    call, so that the fp16x3 path splits `adj` once for both GEMMs.  want_bias: also the bias
+    gradient adj.sum(0) (autodiff.pyx:84) from the same pass over adj -> (dx, dw, db)."""
     cdef ndarray a = _as_device(adj)._compact()
     cdef ndarray xx = _as_device(x)._compact()
     cdef ndarray ww = _as_device(w)._compact()
@@ -1304,6 +1305,12 @@ def linear_bwd(adj, x, w):
     cdef ndarray dw = _new_array(2, shp, SK_F32)
     cdef sk_array da, dxx, dww, ddx, ddw
     a._desc(&da); xx._desc(&dxx); ww._desc(&dww); dx._desc(&ddx); dw._desc(&ddw)
+    cdef ndarray db
+    if want_bias:
+        shp[0] = a._shape[1]
+        db = _new_array(1, shp, SK_F32)
+        _check(sk_linear_bwd_bias(&da, &dxx, &dww, &ddx, &ddw, <float *> db._ptr))
+        return dx, dw, db
     _check(sk_linear_bwd(&da, &dxx, &dww, &ddx, &ddw))
     return dx, dw
 

@@ -198,7 +198,21 @@ int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias, sk
   return matmul_impl(x, w, bias, out, epilogue, algo);
 }
 
+static int linear_bwd_impl(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw,
+                           float *db);
+
 int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw) {
+  return linear_bwd_impl(adj, x, w, dx, dw, nullptr);
+}
+
+int sk_linear_bwd_bias(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw,
+                       float *db) {
+  SK_REQUIRE(db != nullptr, "sk_linear_bwd_bias: null db");
+  return linear_bwd_impl(adj, x, w, dx, dw, db);
+}
+
+static int linear_bwd_impl(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw,
+                           float *db) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(adj && x && w && dx && dw, "sk_linear_bwd: null array");
@@ -215,8 +229,12 @@ int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_
   if (plain) {
     bool done = false;
     rc = linear_bwd_f16x3((const float *)adj->data, (const float *)x->data, (const float *)w->data,
-                          (float *)dx->data, (float *)dw->data, Bn, I, O, &done);
+                          (float *)dx->data, (float *)dw->data, db, Bn, I, O, &done);
     if (rc || done) return rc;
+  }
+  if (db) {   // general path: the bias gradient is its own column-sum pass
+    SK_REQUIRE(adj->dtype == SK_F32 && is_contiguous(adj), "sk_linear_bwd_bias: adj must be contiguous float32");
+    if ((rc = sk_colsum((const float *)adj->data, nullptr, db, Bn, O))) return rc;
   }
   // general path: two GEMMs on .T views (backward.pyx:720-736)
   sk_array wt = *w, xt = *x;

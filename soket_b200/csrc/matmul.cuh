@@ -35,7 +35,7 @@ bool tc_supported(const GemmProblem &g, int algo);
 bool tc_operand_ok(int64_t mn, int64_t k, int64_t s_mn, int64_t s_k, int es, const void *ptr);
 bool tc_profitable(const GemmProblem &g);
 int launch_gemm_tc(const GemmProblem &g, int algo);
-int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx, float *dw, int64_t Bn,
+int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx, float *dw, float *db, int64_t Bn,
                      int64_t I, int64_t O, bool *done);
 
 }  // namespace sk

@@ -59,11 +59,18 @@ __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s
 template <int TPR, int VPT>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ hi, __half *__restrict__ lo,
-                  int64_t ldh, float *__restrict__ inv_scale, int64_t outer, int inner) {
+                  int64_t ldh, float *__restrict__ inv_scale, int64_t outer, int inner,
+                  float *__restrict__ cs_part) {
   __shared__ float red[8];
   constexpr int RPB = 256 / TPR;
   const int t = threadIdx.x % TPR, grp = threadIdx.x / TPR;
   const int units = (int)(ldh >> 3);
+  // by-product for Linear backward: column sums of the UNSCALED operand (the bias gradient,
+  // autodiff.pyx:84) -- a thread always visits the same columns, so it keeps their running sums
+  // and writes one partial row per thread group at the end (cs_part: (gridDim.x * RPB, ldh))
+  float4 ca[VPT], cb[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) { ca[j] = make_float4(0.f, 0.f, 0.f, 0.f); cb[j] = ca[j]; }
   for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < outer; row0 += (int64_t)gridDim.x * RPB) {
     const int64_t row = row0 + grp;
     const bool live = row < outer;
@@ -89,6 +96,10 @@ split_rows_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__
           if (c + 6 < inner) b[j].z = xr[c + 6];
         }
         m = absmax4(absmax4(m, a[j]), b[j]);
+        if (cs_part) {
+          ca[j].x += a[j].x; ca[j].y += a[j].y; ca[j].z += a[j].z; ca[j].w += a[j].w;
+          cb[j].x += b[j].x; cb[j].y += b[j].y; cb[j].z += b[j].z; cb[j].w += b[j].w;
+        }
       }
     }
     m = warp_max(m);
@@ -113,6 +124,43 @@ split_rows_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__
         *reinterpret_cast<uint4 *>(lo + row * ldh + (int64_t)u * 8) = l;
       }
     }
+  }
+  if (cs_part) {
+    float *pr = cs_part + ((int64_t)blockIdx.x * RPB + grp) * ldh;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int u = t + j * TPR;
+      if (u < units) {
+        *reinterpret_cast<float4 *>(pr + (int64_t)u * 8) = ca[j];
+        *reinterpret_cast<float4 *>(pr + (int64_t)u * 8 + 4) = cb[j];
+      }
+    }
+  }
+}
+
+// column sums of the (P x ld) partial matrix above (L2 resident: just written).  Block = 8 float4
+// column groups x 32 row lanes; the 32 lane sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_partials_kernel(const float *__restrict__ part, int64_t P, int64_t ld, float *__restrict__ out, int64_t C) {
+  __shared__ float4 sm[32][8];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int64_t c = ((int64_t)blockIdx.x * 8 + cg) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < ld) {
+    for (int64_t r = rl; r < P; r += 32) {
+      const float4 v = *reinterpret_cast<const float4 *>(part + r * ld + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sm[rl][cg] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x >> 2, k = threadIdx.x & 3;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += reinterpret_cast<const float *>(&sm[i][g])[k];
+    const int64_t cc = ((int64_t)blockIdx.x * 8 + g) * 4 + k;
+    if (cc < C) out[cc] = t;
   }
 }
 
@@ -253,8 +301,14 @@ void SplitOperand::release() {
 
 // x: `outer` stored rows of `inner` contiguous fp32 (pitch ldx, 16-byte aligned base and
 // pitch).  scale_rows: one scale per stored row (K-major operand), else per stored column.
+bool split_colsum_supported(int64_t inner) { return (inner + 7) / 8 <= 1024; }
+
 int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool scale_rows, SplitOperand &out,
-              const float *row_mul) {
+              const float *row_mul, float *colsum_out) {
+  if (colsum_out && (!scale_rows || !split_colsum_supported(inner))) {
+    set_error("split_f16: column sums come with the row-scaled split of rows up to 8192 elements only");
+    return SK_ERR_ARG;
+  }
   if (scale_rows && row_mul) {
     set_error("split_f16: row multipliers apply to the column-scaled (MN-major) case only");
     return SK_ERR_ARG;
@@ -272,11 +326,18 @@ int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool sc
   if ((rc = sk_malloc((size_t)n_scale * (scale_rows ? 4 : 8), (void **)&out.inv_scale))) { out.release(); return rc; }
   if (scale_rows) {
     const int64_t units = ldh / 8;
+    float *cs_part = nullptr;
+    int64_t cs_rows = 0;
+    // with column sums: fewer, longer-running blocks keep the partial matrix small (4 per SM)
 #define ROWS(TPR, VPT)                                                                                  \
   do {                                                                                                  \
-    const int grid = grid_for(outer, 256 / TPR, 16);                                                    \
+    const int grid = grid_for(outer, 256 / TPR, colsum_out ? 4 : 16);                                   \
+    if (colsum_out) {                                                                                   \
+      cs_rows = (int64_t)grid * (256 / TPR);                                                            \
+      if ((rc = sk_malloc((size_t)(cs_rows * ldh) * sizeof(float), (void **)&cs_part))) { out.release(); return rc; } \
+    }                                                                                                   \
     split_rows_kernel<TPR, VPT><<<grid, 256, 0, stream()>>>(x, ldx, out.hi, out.lo, ldh, out.inv_scale, \
-                                                            outer, (int)inner);                         \
+                                                            outer, (int)inner, cs_part);                \
   } while (0)
     if (units <= 32) ROWS(32, 1);
     else if (units <= 64) ROWS(32, 2);
@@ -290,6 +351,11 @@ int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool sc
     }
 #undef ROWS
     SK_LAUNCH_CHECK();
+    if (cs_part) {
+      colsum_partials_kernel<<<(unsigned)((ldh / 4 + 7) / 8), 256, 0, stream()>>>(cs_part, cs_rows, ldh, colsum_out, inner);
+      SK_LAUNCH_CHECK();
+      sk_free(cs_part);   // stream-ordered
+    }
   } else {
     uint32_t *colmax = (uint32_t *)(out.inv_scale + n_scale);
     SK_CUDA(cudaMemsetAsync(colmax, 0, (size_t)n_scale * 4, stream()));

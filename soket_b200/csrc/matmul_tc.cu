@@ -530,9 +530,10 @@ int launch_gemm_tc(const GemmProblem &g0, int algo) {
 // X'[b, i] = X[b, i] * 2^-e_b (exact), split by columns.  One split pass over adj (12 B/elem
 // for the separate column split) disappears per layer.  All three matrices row-major
 // contiguous, pitches multiples of 16 bytes.  *done = false: shapes not eligible, nothing ran.
-int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx, float *dw, int64_t Bn,
-                     int64_t I, int64_t O, bool *done) {
+int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx, float *dw, float *db,
+                     int64_t Bn, int64_t I, int64_t O, bool *done) {
   *done = false;
+  static const bool fuse_colsum = !(getenv("SOKET_B200_FUSE_COLSUM") && !strcmp(getenv("SOKET_B200_FUSE_COLSUM"), "0"));
   GemmProblem gx, gw;
   memset(&gx, 0, sizeof(gx));
   memset(&gw, 0, sizeof(gw));
@@ -545,7 +546,10 @@ int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx
   SplitOperand sa, sw, sx;
   {
     ProfScope pp(SK_PROF_GEMM_PREP, 8.0 * ((double)Bn * O + (double)I * O + (double)Bn * I));
-    if ((rc = split_f16(adj, O, Bn, O, true, sa))) return rc;
+    // db = column sums of adj (autodiff.pyx:84) ride along with the row split of adj when they can
+    const bool db_here = db && fuse_colsum && split_colsum_supported(O);
+    if ((rc = split_f16(adj, O, Bn, O, true, sa, nullptr, db_here ? db : nullptr))) return rc;
+    if (db && !db_here && (rc = sk_colsum(adj, nullptr, db, Bn, O))) { sa.release(); return rc; }
     if ((rc = split_f16(w, O, I, O, true, sw))) { sa.release(); return rc; }                    // W rows = N index of dX
     if ((rc = split_f16(x, I, Bn, I, false, sx, sa.inv_scale))) { sa.release(); sw.release(); return rc; }
   }

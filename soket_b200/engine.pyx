@@ -1105,10 +1105,16 @@ class _LinearOp(Op):
         a2 = adj if adj.ndim == 2 else B.reshape(adj, (-1, adj.shape[-1]))
         x2 = x._data if x._data.ndim == 2 else B.reshape(x._data, (-1, x.shape[-1]))
         gx = None
+        want_b = b is not None and b.requires_grad
         if x.requires_grad and w.requires_grad:
-            gx, gw = B.linear_bwd(a2, x2, w._data)     # one split of adj shared by both GEMMs
+            if want_b:     # one split of adj shared by both GEMMs, its column sums = the bias gradient
+                gx, gw, gb = B.linear_bwd(a2, x2, w._data, True)
+            else:
+                gx, gw = B.linear_bwd(a2, x2, w._data)
+                gb = None
             if x._data.ndim != 2:
                 gx = B.reshape(gx, x.shape)
+            return (gx, gw, gb)
         else:
             if x.requires_grad:
                 gx = B.matmul(a2, w._data.T)

@@ -257,3 +257,23 @@ def test_linear_bwd_shared_split(sk, Bn, I, O, dist):
     assert dx.shape == (Bn, I) and dw.shape == (I, O)
     assert err_ratio(dx, adj, np.ascontiguousarray(w.T)) <= 2e-6
     assert err_ratio(dw, np.ascontiguousarray(x.T), adj) <= 2e-6
+
+
+@pytest.mark.parametrize("B_,I,O", [(8192, 4096, 4096), (1024, 512, 1024), (300, 256, 512), (50, 20, 30), (4096, 4096, 8)])
+def test_linear_bwd_bias_gradient_from_the_adj_split(sk, B_, I, O):
+    """sk_linear_bwd_bias: db = adj.sum(0) (autodiff.pyx:84) as a by-product of the row split of adj
+    on the fp16x3 path (and from sk_colsum on the general path); dX / dW unchanged by it."""
+    rng = np.random.default_rng(B_ + I + O)
+    adj = rng.standard_normal((B_, O)).astype("float32") * np.exp(rng.standard_normal((B_, 1))).astype("float32")
+    x = rng.standard_normal((B_, I)).astype("float32")
+    w = (rng.standard_normal((I, O)) / np.sqrt(I)).astype("float32")
+    d_adj, d_x, d_w = sk.array(adj), sk.array(x), sk.array(w)
+    dx, dw, db = sk.linear_bwd(d_adj, d_x, d_w, True)
+    dx0, dw0 = sk.linear_bwd(d_adj, d_x, d_w)
+    assert np.array_equal(sk.asnumpy(dx), sk.asnumpy(dx0)) and np.array_equal(sk.asnumpy(dw), sk.asnumpy(dw0))
+    got = sk.asnumpy(db)
+    assert got.shape == (O,) and got.dtype == np.float32
+    want = adj.astype(np.float64).sum(0)
+    bound = np.abs(adj).astype(np.float64).sum(0)
+    assert np.all(np.abs(got - want) <= 1e-6 * bound + 1e-30)       # fp32 tree sum against float64
+    assert np.abs(got - adj.sum(0)).max() <= 1e-5 * np.abs(want).max()
