@@ -44,8 +44,14 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly ONE JSON line (the driver parses it): keep a private handle to the real
 # stdout and point fd 1 at stderr, so that banners printed by libraries at the C level (e.g.
 # "NCCL version ..." when NCCL_DEBUG is set in the environment) cannot land in front of it.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_JSON_OUT = sys.stdout       # main() swaps in the private handle; importers keep plain stdout
+
+
+def _isolate_stdout():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 DIM, HIDDEN, BLOCKS, CLASSES = 784, 4096, 8, 10
 BATCH_PER_GPU = 8192
@@ -472,6 +478,7 @@ def main():
     ap.add_argument("--norm", default="layer", choices=["layer", "batch"],
                     help="normalisation of the residual blocks (the bench line is LayerNorm, as examples/mlp_resnet/model.py)")
     args = ap.parse_args()
+    _isolate_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     global NORM
