@@ -2,29 +2,34 @@
 """bench.py -- MLPResNet training throughput on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's own CPU path
+    python bench.py --impl dropin --steps K ...                # the UNMODIFIED reference on soket.gpu()
     torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU, NCCL
 
-Workload (BASELINE.json configs[3]/[4]): the wide MLPResNet of
-examples/mlp_resnet/model.py -- 784 -> 4096, 8 residual blocks (Linear, LayerNorm,
-ReLU, Dropout(0.01), Linear, LayerNorm; residual add; ReLU), -> 10 classes -- in the
-`self.fn`-retaining variant that makes all 68 tensors (271.9 M parameters) trainable
-(quirk Q1), batch 8192 PER GPU, Adam(lr=1e-3), fp32, synthetic MNIST-shaped data,
-random-init weights (kaiming_normal, quirk Q9).  One step = forward + softmax-CE +
-backward + Adam update.  Data-parallel runs (N > 1) keep 8192 rows per GPU (weak
-scaling) and all-reduce every gradient over NCCL, overlapped with backward.
+Workload (BASELINE.json configs[3] / [4]): the wide MLPResNet of
+examples/mlp_resnet/model.py -- 784 -> 4096, 8 residual blocks (Linear, LayerNorm, ReLU,
+Dropout(0.01), Linear, LayerNorm; residual add; ReLU), -> 10 classes -- in the `self.fn`-retaining
+variant that makes all 68 tensors (271.9 M parameters) trainable (quirk Q1; `--verbatim-q1` runs
+the 4-tensor model as written), GLOBAL batch 8192, Adam(lr=1e-3), fp32, synthetic MNIST-shaped
+data, random-init weights (kaiming_normal, quirk Q9).  One step = forward + softmax-CE + backward
++ Adam update.  Data-parallel runs (N > 1) SPLIT the global batch (rank r takes rows
+[r B/N, (r+1) B/N): strong scaling, as section 8e defines the configuration) and all-reduce every
+gradient over NCCL, bucketed and overlapped with backward; `--scaling weak` keeps 8192 rows per
+GPU instead.
 
 One JSON line on stdout (rank 0):
   value      samples/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e        samples/s through the public API with per-step pinned-host -> device
-             copies of the batch and a device -> host read of the loss
-  roofline   the dominant kernel (the tcgen05 GEMM): achieved algorithmic TFLOP/s
-             (2*M*N*K), measured live with CUDA events around every GEMM kernel launch
-             of K steps, against the measured bf16 tensor peak of MEASURED_PEAKS.json;
-             `traffic` = DRAM bytes per launch of that kernel from the committed ncu
-             --set full capture (profiles/*_kernel_traffic.json)
-  cpu_baseline  the reference (oracle/_ref, else the NumPy port) on the host cores,
-             on a bounded sample of the same workload (rank 0, N = 1 only)
+  e2e        samples/s through the public API with per-step pinned-host -> device copies of the
+             batch and a device -> host read of the loss
+  roofline   the dominant kernel (the tcgen05 GEMM): achieved algorithmic TFLOP/s (2*M*N*K), measured
+             live with CUDA events around every GEMM kernel launch of K steps, against the measured
+             bf16 tensor peak of MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch of that
+             kernel from the committed ncu --set full capture (profiles/*_kernel_traffic.json)
+  cpu_baseline  the reference (oracle/_ref, else the NumPy port) on the host cores, on a bounded
+             sample of the same workload (rank 0, N = 1 only)
+  parity_check  (N = 1) one step of THIS model on the sample's rows against the reference's own
+             step from identical weights: loss, three gradient norms, three parameter norms
+  dp_check   (N > 1) a checksum of every parameter after the timed loops, identical on all ranks
 """
 from __future__ import annotations
 
@@ -36,7 +41,15 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The CPU legs (the reference arm; the cpu_baseline leg of a 1-GPU run) use every host core.
+# torchrun exports OMP_NUM_THREADS=1 to its workers, and OpenBLAS reads its thread count when NumPy
+# is first imported: decide it here, before that import.
+_NCPU = os.cpu_count() or 1
+if "reference" in sys.argv or os.environ.get("WORLD_SIZE", "1") == "1":
+    os.environ["OPENBLAS_NUM_THREADS"] = str(_NCPU)
+    os.environ["OMP_NUM_THREADS"] = str(_NCPU)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -53,11 +66,13 @@ def _isolate_stdout():
     _JSON_OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
 
+
 DIM, HIDDEN, BLOCKS, CLASSES = 784, 4096, 8, 10
-BATCH_PER_GPU = 8192
+GLOBAL_BATCH = 8192
 DROP_P = 0.01
 LR = 1e-3
 NORM = "layer"
+METRIC = "mlpresnet_train_samples_per_s"
 
 
 def flops_per_step(batch, hidden=HIDDEN, blocks=BLOCKS, dim=DIM, classes=CLASSES):
@@ -65,6 +80,26 @@ def flops_per_step(batch, hidden=HIDDEN, blocks=BLOCKS, dim=DIM, classes=CLASSES
     fwd = 2.0 * batch * (dim * hidden + blocks * 2 * hidden * hidden + hidden * classes)
     bwd = 2.0 * batch * (dim * hidden + blocks * 2 * 2 * hidden * hidden + 2 * hidden * classes)
     return fwd + bwd
+
+
+def read_env():
+    """RANK / LOCAL_RANK / WORLD_SIZE as torchrun sets them (no package import: the reference arm
+    must not load the product)."""
+    class Env:
+        rank = int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        master_addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+        master_port = int(os.environ.get("MASTER_PORT", "29500"))
+    return Env()
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------- clocks
@@ -124,17 +159,19 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- model builders
-def build_model(nn, hidden, blocks, drop_p=DROP_P, norm="layer"):
-    """examples/mlp_resnet/model.py:17-58 out of the given `nn` namespace (the
-    reference's soket.nn or soket_b200.nn), keeping `self.fn` so the inner layers are
-    visible to parameters() / modules() / train() (quirk Q1)."""
+def build_model(nn, hidden, blocks, drop_p=DROP_P, norm="layer", retain_fn=True):
+    """examples/mlp_resnet/model.py:17-58 out of the given `nn` namespace (the reference's soket.nn
+    or soket_b200.nn).  retain_fn keeps `self.fn`, which makes the inner layers visible to
+    parameters() / modules() / train() (quirk Q1); False is the model exactly as written there
+    (4 trainable tensors: the first and last Linear)."""
     class ResidualBlock(nn.Sequential):
         def __init__(self, dim, hid):
             Norm = nn.LayerNorm if norm == "layer" else nn.BatchNorm1d
             fn = nn.Sequential(nn.Linear(dim, hid), Norm(hid), nn.ReLU(), nn.Dropout(p=drop_p),
                                nn.Linear(hid, hid), Norm(hid))
             super().__init__(nn.Residual(fn), nn.ReLU())
-            self.fn = fn
+            if retain_fn:
+                self.fn = fn
 
     class MLPResNet(nn.Sequential):
         def __init__(self):
@@ -170,82 +207,148 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-# --------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step_time(batch, steps, warmup, hidden=HIDDEN, blocks=BLOCKS):
-    """Time the reference's own CPU implementation (oracle/_ref) -- or, if it is not
-    built, the NumPy port -- on `batch` rows of the same model.  Returns
-    (seconds_per_step, kind, cores)."""
-    from oracle import ref_model
-    cores = os.cpu_count() or 1
-    soket = ref_model.import_reference()
-    X, y = synthetic_batch(batch, 0)
-    if soket is not None:
-        import soket.nn as rnn
-        from soket.nn.init import kaiming_normal
-        from soket.optim import Adam
-        np.random.seed(0)
-        model = build_model(rnn, hidden, blocks, norm=NORM)
-        for m in model.modules():
-            if type(m).__name__ == "Linear":
-                kaiming_normal(m.weight)
-        opt = Adam(model.parameters(), lr=LR)
-        crit = rnn.SoftmaxCrossEntropyLoss()
-        model.train(True)
-        Xt, yt = soket.Tensor(X), soket.Tensor(y)
+def workload_config(args, world, per_gpu, impl="ours"):
+    trainable = (4 + 8 * args.blocks) if not args.verbatim_q1 else 4
+    cfg = {
+        "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, "
+                    f"{'LayerNorm' if args.norm == 'layer' else 'BatchNorm1d'}, "
+                    f"dropout={DROP_P}) train step, Adam lr=1e-3, fp32, {trainable} trainable tensors "
+                    f"(BASELINE.json configs[3]; configs[4] for N>1)",
+        "global_batch": per_gpu * world, "batch_per_gpu": per_gpu,
+        "parallelism": f"dp{world}" if world > 1 else "single",
+        "l2": "per-step working set (activations + 1.09 GB of weights) >> 126 MB L2; no explicit flush",
+    }
+    if impl == "reference":
+        cfg["cpu_sample_rows_per_step"] = args.cpu_sample_batch
+    return cfg
 
-        def step():
-            loss = crit(model(Xt), yt)
-            loss.backward()
-            opt.step()
-            return loss.item()
-        kind = "reference"
-    else:
-        from oracle import soket_np as O
-        om = O.MLPResNet(DIM, hidden, blocks, CLASSES, norm="layer")
-        om.init_kaiming(0)
-        opt = O.Adam(len(om.names()), lr=LR)
 
-        def step():
-            return om.train_step(X, y, opt)[0]
-        kind = "port"
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    return (time.perf_counter() - t0) / max(steps, 1), kind, cores
+# --------------------------------------------------------------------------- CPU reference
+class CpuReference:
+    """The reference's own CPU implementation of the step (oracle/_ref), else the NumPy port."""
+
+    def __init__(self, args, install_compat):
+        from oracle import ref_model
+        self.ref_model = ref_model
+        self.soket = ref_model.import_reference(install_compat=install_compat)
+        self.kind = "reference" if self.soket is not None else "port"
+        self.cores = _NCPU
+        hidden, blocks = args.hidden, args.blocks
+        if self.soket is not None:
+            import soket.nn as rnn
+            from soket.nn.init import kaiming_normal
+            from soket.optim import Adam
+            np.random.seed(0)
+            self.model = build_model(rnn, hidden, blocks, norm=args.norm, retain_fn=not args.verbatim_q1)
+            for m in self.model.modules():
+                if type(m).__name__ == "Linear":
+                    kaiming_normal(m.weight)
+            self.params = list(self.model.parameters())
+            self.opt = Adam(self.model.parameters(), lr=LR)
+            self.crit = rnn.SoftmaxCrossEntropyLoss()
+            self.model.train(True)
+        else:
+            from oracle import soket_np as O
+            self.om = O.MLPResNet(DIM, hidden, blocks, CLASSES, norm="layer")
+            self.om.init_kaiming(0)
+            self.oopt = O.Adam(len(self.om.names()), lr=LR)
+
+    def set_batch(self, X, y):
+        self.X, self.y = X, y
+        if self.soket is not None:
+            self.Xt, self.yt = self.soket.Tensor(X), self.soket.Tensor(y)
+
+    def step(self):
+        if self.soket is None:
+            return self.om.train_step(self.X, self.y, self.oopt)[0]
+        loss = self.crit(self.model(self.Xt), self.yt)
+        loss.backward()
+        self.opt.step()
+        return loss.item()
+
+    def numpy_params(self):
+        return [self.ref_model.to_numpy(self.soket, p) for p in self.params]
+
+    def numpy_grads(self, idx):
+        return [self.ref_model.to_numpy(self.soket, self.params[i].grad) for i in idx]
+
+    def time_steps(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        return (time.perf_counter() - t0) / max(steps, 1)
 
 
 def run_reference(args, env):
     if env.rank != 0:
         return
     sample = args.cpu_sample_batch
-    sec, kind, cores = cpu_reference_step_time(sample, args.steps, min(args.warmup, 1))
+    ref = CpuReference(args, install_compat=False)
+    assert "soket_b200" not in sys.modules, "the reference arm must not load the product"
+    ref.set_batch(*synthetic_batch(sample, 0))
+    sec = ref.time_steps(args.steps, args.warmup)
     value = sample / sec
     line = {
-        "impl": "reference", "metric": "mlpresnet_train_samples_per_s", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} Adam step(s) of the same model on {sample} rows per step "
-                                   f"(full batch is {BATCH_PER_GPU}; the fixed per-step Adam cost is amortised over the sample, "
-                                   f"full-batch CPU throughput is ~15 % higher); NumPy/OpenBLAS threads = all host cores"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1, args.global_batch, "reference"),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": ref.cores, "kind": ref.kind,
+                         "blas_threads": blas_threads(),
+                         "env": {k: os.environ.get(k) for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS")},
+                         "sample": f"{args.steps} Adam step(s) of the same model on {sample} rows per step after "
+                                   f"{args.warmup} warm-up step(s) (the full batch is {args.global_batch} rows: "
+                                   f"--cpu-sample-batch {args.global_batch} --steps 3 times it whole; the per-step Adam "
+                                   f"update over 272 M parameters does not shrink with the sample, so full-batch CPU "
+                                   f"throughput is ~15 % higher than this sample's); NumPy/OpenBLAS on all host cores"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def workload_config(args, world):
-    return {
-        "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, "
-                    f"{'LayerNorm' if args.norm == 'layer' else 'BatchNorm1d'}, "
-                    f"dropout={DROP_P}) train step, Adam lr=1e-3, fp32, all {4 + 8 * args.blocks} tensors trainable "
-                    f"(BASELINE.json configs[3]; configs[4] for N>1)",
-        "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-        "parallelism": f"dp{world}" if world > 1 else "single",
-        "l2": "per-step working set (activations + 1.09 GB of weights) >> 126 MB L2; no explicit flush",
+# --------------------------------------------------------------------------- parity check (N = 1)
+def parity_check(args, ref, sk, soket, nn, Adam):
+    """One dropout-free step on the CPU sample's rows, from the reference's own initial weights, on
+    both sides (the reference's step doubles as the cpu_baseline leg's warm-up): loss, three
+    gradient norms and three parameter norms after the Adam update."""
+    if ref.soket is None:
+        return {"skipped": "oracle/_ref is not built (NumPy port only)"}
+    X, y = ref.X, ref.y
+    model = build_model(nn, args.hidden, args.blocks, norm=args.norm, retain_fn=not args.verbatim_q1)
+    params = list(model.parameters())
+    want0 = ref.numpy_params()
+    assert len(params) == len(want0)
+    for p, w in zip(params, want0):
+        assert tuple(p.shape) == tuple(w.shape), (p.shape, w.shape)
+        p.data = soket.Tensor(w)
+    del want0
+    opt = Adam(params, lr=LR)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    model.train(False)          # Dropout off on both sides (reachable through self.fn, quirk Q1)
+    ref.model.train(False)
+    loss = crit(model(soket.Tensor(X)), soket.Tensor(y))
+    loss.backward()
+    pick = sorted({0, len(params) // 2, len(params) - 2})       # first weight, a middle tensor, last weight
+    gnorm_dev = [float(np.linalg.norm(params[i].grad.numpy().astype(np.float64))) for i in pick]
+    opt.step()
+    loss_dev = float(loss.item())
+    loss_ref = float(ref.step())
+    ref.model.train(True)
+    gnorm_ref = [float(np.linalg.norm(g.astype(np.float64))) for g in ref.numpy_grads(pick)]
+    pnorm_dev = [float(np.linalg.norm(params[i].numpy().astype(np.float64))) for i in pick]
+    pnorm_ref = [float(np.linalg.norm(ref.ref_model.to_numpy(ref.soket, ref.params[i]).astype(np.float64))) for i in pick]
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-30)
+    out = {
+        "rows": int(X.shape[0]), "tensors": pick,
+        "loss": {"device": loss_dev, "reference": loss_ref, "rel_err": rel(loss_dev, loss_ref)},
+        "grad_norm_rel_err": [rel(a, b) for a, b in zip(gnorm_dev, gnorm_ref)],
+        "param_norm_rel_err": [rel(a, b) for a, b in zip(pnorm_dev, pnorm_ref)],
     }
+    out["ok"] = bool(out["loss"]["rel_err"] <= 1e-5 and max(out["grad_norm_rel_err"]) <= 1e-4
+                     and max(out["param_norm_rel_err"]) <= 1e-5)
+    return out
 
 
 # --------------------------------------------------------------------------- our arm
@@ -259,8 +362,13 @@ def run_ours(args, env):
     sk.init(env.local_rank)
     rdv = dp.Rendezvous(env) if env.world > 1 else None
 
+    strong = args.scaling == "strong"
+    if strong and args.global_batch % env.world:
+        raise SystemExit(f"global batch {args.global_batch} does not split over {env.world} ranks")
+    batch = args.global_batch // env.world if strong else args.global_batch     # rows per GPU
+
     sk.random.seed(1234)          # identical initial weights on every rank
-    model = build_model(nn, args.hidden, args.blocks, norm=args.norm)
+    model = build_model(nn, args.hidden, args.blocks, norm=args.norm, retain_fn=not args.verbatim_q1)
     for m in model.modules():
         if type(m).__name__ == "Linear":
             nn.kaiming_normal(m.weight)
@@ -273,8 +381,13 @@ def run_ours(args, env):
     model.train(True)
     sk.random.seed(99 + env.rank)  # dropout masks differ per rank
 
-    batch = args.batch
-    Xh, yh = synthetic_batch(batch, 100 + env.rank)
+    if strong:      # rank r takes rows [r B/W, (r+1) B/W) of ONE global batch (section 8e)
+        Xg, yg = synthetic_batch(args.global_batch, 100)
+        rows = dp.shard_rows(args.global_batch, env.rank, env.world)
+        Xh, yh = np.ascontiguousarray(Xg[rows]), np.ascontiguousarray(yg[rows])
+        del Xg, yg
+    else:
+        Xh, yh = synthetic_batch(batch, 100 + env.rank)
     Xd, yd = soket.Tensor(Xh), soket.Tensor(yh)
     pin_x = sk.PinnedBuffer(Xh.shape, "float32"); pin_x.array[...] = Xh
     pin_y = sk.PinnedBuffer(yh.shape, "uint8"); pin_y.array[...] = yh
@@ -288,8 +401,7 @@ def run_ours(args, env):
     def step_resident():
         loss = crit(model(Xd), yd)
         loss.backward()
-        ddp.finish()
-        opt.step()
+        ddp.step()               # joins the gradient all-reduces bucket by bucket, then updates
         return loss
 
     def step_e2e():
@@ -306,8 +418,7 @@ def run_ours(args, env):
         pin_y.prefetch_to_device(stage_y[(k + 1) % 2])
         loss = crit(model(E.Tensor._const(stage_x[k % 2])), E.Tensor._const(stage_y[k % 2]))
         loss.backward()
-        ddp.finish()
-        opt.step()
+        ddp.step()
         # the loss of EVERY step is read back to the host; the read of step k is consumed while
         # step k+1 is being enqueued (the host runs one step ahead instead of draining the GPU)
         pin_loss[k % 2].copy_from_device(loss._data.reshape(1))
@@ -400,9 +511,21 @@ def run_ours(args, env):
     ms_e2e = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3)   # device events vs host wall clock
     clock_info = clocks.stop() if env.rank == 0 else None
 
+    dp_check = None
     if rdv is not None:
         ms = max(rdv.all_gather_float(ms))
         ms_e2e = max(rdv.all_gather_float(ms_e2e))
+        # replicated weights must still be replicated: one fp32 sum per parameter (the same
+        # reduction kernel on every rank), hashed, compared across ranks
+        import hashlib
+        sums = np.array([float(sk.asnumpy(sk.sum(p._data)).reshape(-1)[0]) for p in params], np.float64)
+        digest = hashlib.sha256(sums.tobytes()).hexdigest()[:16]
+        digests = rdv.all_gather_str(digest)
+        losses = rdv.all_gather_float(float(loss_value))
+        dp_check = {"param_checksum": digest, "identical_on_all_ranks": len(set(digests)) == 1,
+                    "ranks": len(digests), "local_loss_per_rank": losses}
+        if len(set(digests)) != 1:
+            print(f"[bench rank {env.rank}] PARAMETER CHECKSUMS DIFFER ACROSS RANKS: {digests}", file=sys.stderr, flush=True)
     ms_per_step = ms / args.steps
     value = batch * env.world / (ms_per_step * 1e-3)
     e2e_value = batch * env.world / (ms_e2e / args.steps * 1e-3)
@@ -415,15 +538,16 @@ def run_ours(args, env):
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         traffic, traffic_src = load_traffic()
         prep = prof.get("gemm_prep", {"ms": 0.0})
+        flop_fams = ("gemm_tc", "gemm_simt")            # work in flops; every other family books bytes
         families = {k: {"launches": v["launches"], "ms_per_step": v["ms"] / args.steps,
-                        "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k.startswith("gemm") else 1e9)) if v["ms"] else 0.0,
-                        "unit": "TFLOP/s" if k.startswith("gemm") else "GB/s"}
+                        "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k in flop_fams else 1e9)) if v["ms"] else 0.0,
+                        "unit": "TFLOP/s" if k in flop_fams else "GB/s"}
                     for k, v in prof.items()}
         line = {
-            "metric": "mlpresnet_train_samples_per_s", "value": value, "unit": "samples/s",
+            "metric": METRIC, "value": value, "unit": "samples/s",
             "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, env.world),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, env.world, batch),
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(Xh.nbytes + yh.nbytes), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
@@ -448,12 +572,23 @@ def run_ours(args, env):
             },
             "kernel_families": families,
             "model_flops_per_step": flops_per_step(batch, args.hidden, args.blocks),
-            "params": n_params, "final_loss": loss_value,
+            "params": n_params, "final_loss": loss_value, "final_loss_e2e": e2e_last_loss,
         }
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         if env.world == 1 and not args.no_cpu_baseline:
-            sec, kind, cores = cpu_reference_step_time(args.cpu_sample_batch, 1, 1, args.hidden, args.blocks)
+            # free the benchmark's device state first: the parity model is a second 272 M-parameter net
+            ref = CpuReference(args, install_compat=True)
+            ref.set_batch(Xh[:args.cpu_sample_batch], yh[:args.cpu_sample_batch])
+            try:
+                line["parity_check"] = parity_check(args, ref, sk, soket, nn, Adam)   # = the CPU leg's warm-up step
+            except Exception as e:      # the bench line must still be printed
+                line["parity_check"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                ref.step()
+            sec = ref.time_steps(1, 0)
             line["cpu_baseline"] = {
-                "value": args.cpu_sample_batch / sec, "unit": "samples/s", "cores": cores, "kind": kind,
+                "value": args.cpu_sample_batch / sec, "unit": "samples/s", "cores": ref.cores, "kind": ref.kind,
+                "blas_threads": blas_threads(),
                 "sample": f"1 Adam step of the same model on {args.cpu_sample_batch} rows after 1 warm-up step "
                           f"(full batch is {batch}; the fixed per-step Adam cost is amortised over the sample, full-batch "
                           f"CPU throughput is ~15 % higher); NumPy/OpenBLAS threads = all host cores"}
@@ -461,15 +596,81 @@ def run_ours(args, env):
     ddp.close()
 
 
+# --------------------------------------------------------------------------- drop-in arm
+def run_dropin(args, env):
+    """The UNMODIFIED reference (oracle/_ref: its Tensor / autodiff / nn / optim code) on
+    `soket.gpu()` with soket_b200 in the CuPy seam (compat.install): every one of the ~1500 array
+    calls per step is one call into libsoketb200.so, nothing fused above the array layer."""
+    if env.rank != 0:
+        return
+    import soket_b200 as sk
+    from oracle import ref_model
+    soket = ref_model.import_reference(install_compat=True)
+    if soket is None:
+        print(json.dumps({"impl": "dropin", "unavailable": "oracle/_ref is not built"}), file=_JSON_OUT, flush=True)
+        return
+    import soket.nn as rnn
+    from soket.nn.init import kaiming_normal
+    from soket.optim import Adam
+    batch = args.global_batch
+    sk.init(env.local_rank)
+    X, y = synthetic_batch(batch, 100)
+    with soket.gpu():
+        np.random.seed(0)
+        model = build_model(rnn, args.hidden, args.blocks, norm=args.norm, retain_fn=not args.verbatim_q1)
+        for m in model.modules():
+            if type(m).__name__ == "Linear":
+                kaiming_normal(m.weight)
+        opt = Adam(model.parameters(), lr=LR)
+        crit = rnn.SoftmaxCrossEntropyLoss()
+        model.train(True)
+        Xt, yt = soket.Tensor(X), soket.Tensor(y)
+
+        def step():
+            loss = crit(model(Xt), yt)
+            loss.backward()
+            opt.step()
+            return loss
+        last = None
+        for _ in range(args.warmup):
+            last = step()
+        sk.synchronize()
+        n0 = sk.launch_count()
+        ev0, ev1 = sk.Event(), sk.Event()
+        ev0.record()
+        for _ in range(args.steps):
+            last = step()
+        ev1.record()
+        ev1.synchronize()
+        ms = ev0.elapsed_ms(ev1) / args.steps
+        launches = sk.launch_count() - n0
+        loss_value = float(last.item())
+    line = {"impl": "dropin", "metric": METRIC, "value": batch / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1, batch), "gpu_launches": int(launches),
+            "launches_per_step": launches / args.steps, "final_loss": loss_value,
+            "note": "the unmodified reference's own Tensor/autodiff/nn/optim code on soket.gpu(); soket_b200 supplies "
+                    "only the array layer (SURVEY.md section 8b seam)"}
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="rows per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "dropin"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the global batch is SPLIT over the ranks (SURVEY.md section 8e, the contract's "
+                         "configuration); weak = every rank gets a full batch")
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH, help="rows per step over all GPUs (strong) / per GPU (weak)")
+    ap.add_argument("--batch", type=int, default=None, help="alias of --global-batch")
     ap.add_argument("--hidden", type=int, default=HIDDEN)
     ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--verbatim-q1", action="store_true",
+                    help="the model exactly as examples/mlp_resnet/model.py writes it: the blocks' inner layers are "
+                         "invisible to parameters() (quirk Q1), 4 trainable tensors / 3.26 M parameters")
     ap.add_argument("--cpu-sample-batch", type=int, default=1024,
                     help="rows per CPU step.  The per-step Adam update (272 M parameters, ~10 s on 8 cores) does not\n"
                          "shrink with the sample, so small samples understate the CPU path: measured on 8 cores\n"
@@ -478,15 +679,18 @@ def main():
     ap.add_argument("--norm", default="layer", choices=["layer", "batch"],
                     help="normalisation of the residual blocks (the bench line is LayerNorm, as examples/mlp_resnet/model.py)")
     args = ap.parse_args()
+    if args.batch is not None:
+        args.global_batch = args.batch
     _isolate_stdout()
-    if args.warmup < 3 and args.impl == "ours":
+    if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     global NORM
     NORM = args.norm
-    from soket_b200 import dp
-    env = dp.read_env()
+    env = read_env()
     if args.impl == "reference":
         run_reference(args, env)
+    elif args.impl == "dropin":
+        run_dropin(args, env)
     else:
         run_ours(args, env)
 

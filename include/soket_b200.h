@@ -29,6 +29,7 @@ extern "C" {
 #define SK_ERR_UNSUPPORTED 3
 #define SK_ERR_NCCL 4
 #define SK_ERR_OOM 5
+#define SK_ERR_INDEX 6 /* an index read by a kernel was out of range (reported at the next sync point) */
 
 #define SK_MAX_NDIM 8
 
@@ -95,6 +96,14 @@ int sk_event_record(void *ev);
 int sk_event_sync(void *ev);
 int sk_event_elapsed_ms(void *start, void *stop, float *ms);
 int sk_event_destroy(void *ev);
+/* The process's streams.  Everything launches on the compute stream unless sk_launch_stream() selects
+ * another one (a host-side switch, single-threaded like the rest of the API): data-parallel training
+ * issues its bucketed all-reduces on the comm stream and the per-bucket optimizer update on the
+ * optimizer stream while backward keeps the compute stream busy. */
+typedef enum { SK_STREAM_COMPUTE = 0, SK_STREAM_COMM = 1, SK_STREAM_COPY = 2, SK_STREAM_OPT = 3 } sk_stream_id;
+int sk_launch_stream(int stream_id);                     /* later launches go to this stream */
+int sk_event_record_on(void *ev, int stream_id);
+int sk_stream_wait_event(int stream_id, void *ev);       /* stream waits for the event (device side) */
 uint64_t sk_launch_count(void); /* kernels this library launched so far */
 int sk_flush_l2(void);          /* overwrite a >L2 scratch buffer */
 
@@ -344,6 +353,11 @@ int sk_nccl_init(int rank, int world, const char id[SK_NCCL_ID_BYTES]);
 int sk_nccl_allreduce(float *buf, size_t count, int on_comm_stream);
 int sk_nccl_broadcast(float *buf, size_t count, int root);
 int sk_nccl_wait(void); /* compute stream waits for the comm stream */
+/* all-reduce(sum) in place on the given stream; ordering is the caller's (events above) */
+int sk_nccl_allreduce_on(float *buf, size_t count, int stream_id);
+/* any NCCL error aborts the communicator (ncclCommAbort) so that the other ranks fail fast instead
+ * of hanging in a collective; sk_nccl_abort does it explicitly */
+int sk_nccl_abort(void);
 int sk_nccl_destroy(void);
 
 #ifdef __cplusplus

@@ -16,8 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 
-def import_reference():
+def import_reference(install_compat=True):
     """Import the built reference package; returns the `soket` module or None.
+    install_compat=False keeps soket_b200 out of the process (bench.py --impl reference: the
+    reference arm must not load the product).
 
     When soket_b200 is importable it is first registered under the module name the
     reference imports for its GPU backend (soket_b200.compat.install), so the same
@@ -25,7 +27,7 @@ def import_reference():
     `soket.gpu()` (the sm_100a kernels -- the drop-in test)."""
     if not os.path.exists(os.path.join(REF_DIR, "soket", "__init__.py")):
         return None
-    if "soket" not in sys.modules:
+    if install_compat and "soket" not in sys.modules:
         try:
             import soket_b200.compat as compat
             compat.install()
@@ -87,3 +89,15 @@ def named_parameters(model, num_blocks):
         out[f"blk{i}.n2.g"], out[f"blk{i}.n2.b"] = g2, b2
     out["out.W"], out["out.b"] = last.weight, last.bias
     return out
+
+
+def to_numpy(soket, t):
+    """A reference Tensor (CPU device) as a NumPy array: the reference has no .numpy(); write it
+    through Tensor.__setitem__ into a from_numpy view (tensor.pyx:484,1092)."""
+    import numpy as np
+    if len(t.shape) == 0:
+        return np.array(t.item(), dtype=str(t.dtype))
+    buf = np.zeros(t.shape, dtype=str(t.dtype))
+    view = soket.Tensor.from_numpy(buf)
+    view[tuple(slice(None) for _ in t.shape)] = t
+    return buf

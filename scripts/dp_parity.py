@@ -23,7 +23,9 @@ def main():
     env = dp.read_env()
     sk.init(env.local_rank)
     rdv = dp.Rendezvous(env)
-    dim, hidden, nb, C, B = 784, 256, 2, 10, 512
+    # DP_WIDE=1: wide enough for the tcgen05 GEMMs / staged LayerNorm kernels of the benchmark
+    wide = os.environ.get("DP_WIDE", "0") == "1"
+    dim, hidden, nb, C, B = (784, 512, 3, 10, 1024) if wide else (784, 256, 2, 10, 512)
     norm = os.environ.get("DP_NORM", "layer")
     # SGD is linear in the gradient: strict multi-step comparison.  Adam's first steps are
     # lr * g / (|g| + eps): elements whose true gradient is zero (every bias in front of a
@@ -46,7 +48,7 @@ def main():
         w = om.params[k] if env.rank == 0 else np.full_like(om.params[k], 7.0)
         t.data = soket.Tensor(w.copy())
     opt = Adam(model.parameters(), lr=1e-3) if use_adam else SGD(model.parameters(), lr=0.05)
-    ddp = dp.DataParallel(opt, rdv)
+    ddp = dp.DataParallel(opt, rdv, bucket_mb=float(os.environ.get("DP_BUCKET_MB", "0.25")))   # several buckets
     ddp.broadcast_parameters(0)
     crit = nn.SoftmaxCrossEntropyLoss()
     oo = O.Adam(len(om.names()), lr=1e-3) if use_adam else O.SGD(len(om.names()), lr=0.05)
@@ -59,9 +61,9 @@ def main():
         y = rng.integers(0, C, B).astype(np.uint8)
         loss = crit(model(soket.Tensor(X[sl])), soket.Tensor(y[sl]))
         loss.backward()
-        ddp.finish()
-        opt.step()
+        ddp.step()               # bucketed all-reduce + per-bucket optimizer update, joined here
         losses.append(loss.item())
+        dev_grads = {k: named[k].grad.numpy() for k in om.names()} if (env.rank == 0 and step == 0) else None
         if env.rank == 0:
             # oracle: W shards, averaged gradients, one step
             acc = None
@@ -74,6 +76,15 @@ def main():
                        else acc[k] + np.asarray(v, dtype=np.float32) / np.float32(env.world) for k, v in g.items()}
             names = om.names()
             gscale = max(float(np.abs(acc[k]).max()) for k in names)
+            if dev_grads is not None:
+                # after step() a parameter's .grad is the SUM over ranks (1/W lives in the optimizer
+                # kernel): element-wise against the oracle's averaged shard gradients
+                for k in names:
+                    got = dev_grads[k].astype(np.float64) / env.world
+                    want = acc[k].astype(np.float64).reshape(got.shape)
+                    rms = float(np.sqrt(np.mean(want * want)))
+                    bound = 1e-5 * np.abs(want) + 2e-5 * rms + 1e-7 * gscale
+                    assert np.all(np.abs(got - want) <= bound), (k, float((np.abs(got - want) / bound).max()))
             signal = {k: np.abs(acc[k]) > 1e-3 * gscale for k in names}   # clear of the rounding-residue floor
             for k, v in zip(names, oo.step([om.params[k] for k in names], [acc[k] for k in names])):
                 om.params[k] = v

@@ -93,6 +93,9 @@ cdef extern from "soket_b200.h" nogil:
     int sk_event_sync(void *ev)
     int sk_event_elapsed_ms(void *start, void *stop, float *ms)
     int sk_event_destroy(void *ev)
+    int sk_launch_stream(int stream_id)
+    int sk_event_record_on(void *ev, int stream_id)
+    int sk_stream_wait_event(int stream_id, void *ev)
     uint64_t sk_launch_count()
     int sk_flush_l2()
 
@@ -189,3 +192,5 @@ cdef extern from "soket_b200.h" nogil:
     int sk_nccl_broadcast(float *buf, size_t count, int root)
     int sk_nccl_wait()
     int sk_nccl_destroy()
+    int sk_nccl_allreduce_on(float *buf, size_t count, int stream_id)
+    int sk_nccl_abort()

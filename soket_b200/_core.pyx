@@ -39,6 +39,8 @@ cdef int _check(int rc) except -1:
         msg = sk_last_error().decode('utf-8', 'replace')
         if rc == 5:
             raise MemoryError(msg)
+        if rc == 6:
+            raise IndexError(msg)
         raise RuntimeError(msg)
     return 0
 
@@ -1211,7 +1213,7 @@ cdef ndarray _mm_operand(ndarray a):
     return a._compact()
 
 
-cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo):
+cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo, object dtype=None):
     cdef ndarray a = _as_device(x)
     cdef ndarray b = _as_device(y)
     cdef ndarray bi = None
@@ -1230,10 +1232,24 @@ cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo
     if a._shape[a._ndim - 1] != b._shape[b._ndim - 2]:
         raise ValueError(f'matmul: input operand 1 has a mismatch in its core dimension 0 '
                          f'(size {b._shape[b._ndim - 2]} is different from {a._shape[a._ndim - 1]})')
-    if a._code != b._code or (a._code != SK_F32 and a._code != SK_BF16):
-        # NumPy would promote; the device GEMMs are fp32 (and bf16-input) only
-        a = _cast_copy(a, SK_F32) if a._code != SK_F32 else a
-        b = _cast_copy(b, SK_F32) if b._code != SK_F32 else b
+    # result dtype = the `dtype=` keyword (forward.pyx:172-178 passes the promoted Tensor dtype) or
+    # NumPy's promotion of the operands; float32 / float16 results are computed by the fp32 GEMMs,
+    # float64 and integer results by the float64 kernel (exact for integers below 2^53)
+    cdef int rcode, ccode
+    if dtype is not None:
+        rcode = _code(dtype)
+    elif a._code == SK_BF16 and b._code == SK_BF16:
+        rcode = SK_F32
+    else:
+        rcode = _code(np.result_type(a._np_dtype, b._np_dtype))
+    if a._code == SK_BF16 and b._code == SK_BF16 and rcode == SK_F32:
+        ccode = SK_BF16
+    else:
+        ccode = SK_F32 if (rcode == SK_F32 or rcode == SK_F16) else SK_F64
+        if ccode == SK_F64 and (bias is not None or epilogue != SK_EPI_NONE):
+            raise TypeError('linear: the fused epilogues are float32 only')
+        a = _cast_copy(a, ccode) if a._code != ccode else a
+        b = _cast_copy(b, ccode) if b._code != ccode else b
     a = _mm_operand(a)
     b = _mm_operand(b)
     nba = a._ndim - 2; nbb = b._ndim - 2
@@ -1248,7 +1264,7 @@ cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo
     shp[nb] = a._shape[a._ndim - 2]
     shp[nb + 1] = b._shape[b._ndim - 1]
     nd = nb + 2
-    out = _new_array(nd, shp, SK_F32)
+    out = _new_array(nd, shp, SK_F64 if ccode == SK_F64 else SK_F32)
     a._desc(&da); b._desc(&db); out._desc(&dout)
     if a._code == SK_BF16:
         algo = SK_MM_BF16
@@ -1260,6 +1276,8 @@ cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo
         _check(sk_linear_fwd(&da, &db, NULL, &dout, epilogue, algo))
     else:
         _check(sk_matmul(&da, &db, &dout, algo))
+    if out._code != rcode:
+        out = _cast_copy(out, rcode)
     if a_vec and b_vec:
         return out._view(0, shp, shp, 0)
     if a_vec:
@@ -1272,7 +1290,7 @@ cdef object _matmul_impl(object x, object y, object bias, int epilogue, int algo
 def matmul(x, y, out=None, dtype=None, algo=None):
     """np.matmul(x, y, dtype='float32') (intern slot _MATMUL; forward.pyx:172-178,
     backward.pyx:720-736).  `.T` views are consumed in place."""
-    return _matmul_impl(x, y, None, SK_EPI_NONE, _DEFAULT_MM_ALGO if algo is None else <int> algo)
+    return _matmul_impl(x, y, None, SK_EPI_NONE, _DEFAULT_MM_ALGO if algo is None else <int> algo, dtype)
 
 
 def linear(x, w, bias=None, relu=False, algo=None):
@@ -1285,7 +1303,7 @@ def linear(x, w, bias=None, relu=False, algo=None):
     return _matmul_impl(x, w, bias, epi, _DEFAULT_MM_ALGO if algo is None else <int> algo)
 
 
-def linear_bwd(adj, x, w, bint want_bias=False):
+def linear_bwd(adj, x, w, bint want_bias=False, out_dw=None, out_db=None):
     """Backward of y = x @ w (backward.pyx:704-742): returns (adj @ w.T, x.T @ adj) from one
     call, so that the fp16x3 path splits `adj` once for both GEMMs.  want_bias: also the bias
     gradient adj.sum(0) (autodiff.pyx:84) from the same pass over adj -> (dx, dw, db)."""
@@ -1302,13 +1320,26 @@ def linear_bwd(adj, x, w, bint want_bias=False):
     shp[0] = xx._shape[0]; shp[1] = xx._shape[1]
     cdef ndarray dx = _new_array(2, shp, SK_F32)
     shp[0] = ww._shape[0]; shp[1] = ww._shape[1]
-    cdef ndarray dw = _new_array(2, shp, SK_F32)
+    # out_dw / out_db: caller-owned result buffers (data-parallel training points them at the slots of
+    # its flat gradient arena, so the all-reduce needs no gather copy)
+    cdef ndarray dw
+    if out_dw is not None:
+        dw = <ndarray> out_dw
+        if dw._code != SK_F32 or dw._ndim != 2 or dw._shape[0] != shp[0] or dw._shape[1] != shp[1] or not dw._is_contiguous():
+            raise ValueError('linear_bwd: out_dw must be a contiguous float32 array of w\'s shape')
+    else:
+        dw = _new_array(2, shp, SK_F32)
     cdef sk_array da, dxx, dww, ddx, ddw
     a._desc(&da); xx._desc(&dxx); ww._desc(&dww); dx._desc(&ddx); dw._desc(&ddw)
     cdef ndarray db
     if want_bias:
         shp[0] = a._shape[1]
-        db = _new_array(1, shp, SK_F32)
+        if out_db is not None:
+            db = <ndarray> out_db
+            if db._code != SK_F32 or db._numel() != shp[0] or not db._is_contiguous():
+                raise ValueError('linear_bwd: out_db must be a contiguous float32 vector of length O')
+        else:
+            db = _new_array(1, shp, SK_F32)
         _check(sk_linear_bwd_bias(&da, &dxx, &dww, &ddx, &ddw, <float *> db._ptr))
         return dx, dw, db
     _check(sk_linear_bwd(&da, &dxx, &dww, &ddx, &ddw))
@@ -1482,9 +1513,17 @@ cdef class Event:
         if self._ev != NULL:
             sk_event_destroy(self._ev)
 
-    def record(self):
-        _check(sk_event_record(self._ev))
+    def record(self, int stream=0):
+        """Record on the compute stream (default) or on STREAM_COMM / STREAM_COPY / STREAM_OPT."""
+        if stream == 0:
+            _check(sk_event_record(self._ev))
+        else:
+            _check(sk_event_record_on(self._ev, stream))
         return self
+
+    def wait(self, int stream=0):
+        """Make `stream` wait (on the device) for this event."""
+        _check(sk_stream_wait_event(stream, self._ev))
 
     def synchronize(self):
         _check(sk_event_sync(self._ev))
@@ -1493,6 +1532,14 @@ cdef class Event:
         cdef float ms = 0
         _check(sk_event_elapsed_ms(self._ev, end._ev, &ms))
         return ms
+
+
+STREAM_COMPUTE, STREAM_COMM, STREAM_COPY, STREAM_OPT = 0, 1, 2, 3
+
+
+def launch_stream(int stream=0):
+    """Kernels launched by later calls go to this stream (host-side switch; see sk_launch_stream)."""
+    _check(sk_launch_stream(stream))
 
 
 def arena_create():

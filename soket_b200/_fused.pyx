@@ -44,16 +44,29 @@ def layernorm_fwd(ndarray x, gamma=None, beta=None, residual=None, double eps=1e
     return y, mean, rstd
 
 
+cdef inline ndarray _vec_out(object out, int64_t cols):
+    """A caller-owned (cols,) float32 result buffer (a slot of the data-parallel gradient arena) or a
+    fresh vector."""
+    cdef ndarray o
+    if out is None:
+        return _new_array(1, &cols, SK_F32)
+    o = <ndarray> out
+    if o._code != SK_F32 or o._numel() != cols or not o._is_contiguous():
+        raise ValueError('expected a contiguous float32 output vector of the parameter\'s length')
+    return o
+
+
 def layernorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd,
-                  y_out=None, int mask_mode=0, bint want_dresidual=False, bint want_params=True):
+                  y_out=None, int mask_mode=0, bint want_dresidual=False, bint want_params=True,
+                  out_dgamma=None, out_dbeta=None):
     """Returns (dx, dgamma, dbeta, dresidual)."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
     cdef ndarray dx = _new_array(x._ndim, x._shape, SK_F32)
     cdef ndarray dg = None, db = None, dres = None
     if want_params:
-        dg = _new_array(1, &cols, SK_F32)
-        db = _new_array(1, &cols, SK_F32)
+        dg = _vec_out(out_dgamma, cols)
+        db = _vec_out(out_dbeta, cols)
     if want_dresidual:
         dres = _new_array(x._ndim, x._shape, SK_F32)
     _check(sk_layernorm_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
@@ -76,15 +89,16 @@ def layernorm_dropout_fwd(ndarray x, gamma, beta, double eps, bint relu, double 
 
 
 def layernorm_dropout_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd, bint relu,
-                          double keep, double r_keep, seed, bint want_params=True):
+                          double keep, double r_keep, seed, bint want_params=True,
+                          out_dgamma=None, out_dbeta=None):
     """Backward of layernorm_dropout_fwd from the adjoint of its output.  Returns (dx, dgamma, dbeta)."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
     cdef ndarray dx = _new_array(x._ndim, x._shape, SK_F32)
     cdef ndarray dg = None, db = None
     if want_params:
-        dg = _new_array(1, &cols, SK_F32)
-        db = _new_array(1, &cols, SK_F32)
+        dg = _vec_out(out_dgamma, cols)
+        db = _vec_out(out_dbeta, cols)
     _check(sk_layernorm_dropout_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
                                     relu, <float> keep, <float> r_keep, <uint64_t> seed, _fptr(dx),
                                     _opt(dg), _opt(db), rows, cols))
@@ -279,6 +293,15 @@ def nccl_init(int rank, int world, bytes uid):
 def nccl_allreduce(ndarray buf, bint on_comm_stream=False):
     """In-place sum all-reduce of a contiguous fp32 buffer."""
     _check(sk_nccl_allreduce(_fptr(buf), <size_t> buf._numel(), on_comm_stream))
+
+
+def nccl_allreduce_on(ndarray buf, int stream):
+    """In-place sum all-reduce on the given stream id; the caller orders it with events."""
+    _check(sk_nccl_allreduce_on(_fptr(buf), <size_t> buf._numel(), stream))
+
+
+def nccl_abort():
+    _check(sk_nccl_abort())
 
 
 def nccl_broadcast(ndarray buf, int root=0):

@@ -46,14 +46,23 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host -> device input prefetch (sk_h2d_prefetch)
+  cudaStream_t opt_stream = nullptr;    // per-bucket optimizer updates of data-parallel training
+  cudaStream_t launch = nullptr;        // where kernels go: `stream` unless sk_launch_stream() says otherwise
 };
 Context &ctx();
 int ensure_init();
 void note_launch();
-inline cudaStream_t stream() { return ctx().stream; }
+inline cudaStream_t stream() { return ctx().launch; }
+cudaStream_t stream_by_id(int id);   // nullptr for an unknown id
 // device-resident counter mixed into dropout seeds at RUN time; a captured graph advances it per replay
 const uint64_t *rng_epoch_ptr();
-void dropout_reseed(uint64_t seed);   // nn_fused.cu: sk_rng_seed also restarts the dropout draw sequence
+void dropout_reseed(uint64_t seed);
+// Sticky device-side error word in mapped pinned host memory: a kernel that meets an invalid index
+// ORs a code into it (the reference raises IndexError at the call; kernels are asynchronous, so it
+// is raised at the next sync point -- sk_sync / sk_d2h / sk_event_sync -- instead).
+enum { SK_DEVERR_LABEL_RANGE = 1 };
+unsigned int *dev_error_ptr();        // device address, for kernels
+int check_dev_error();                // host: SK_OK, or SK_ERR_INDEX after clearing the word   // nn_fused.cu: sk_rng_seed also restarts the dropout draw sequence
 
 // ---- per-family profiling (sk_prof_*) -------------------------------------------
 // Usage inside a launcher:  ProfScope ps(SK_PROF_GEMM_TC, flops);  ... launch ...

@@ -24,6 +24,7 @@ struct NcclApi {
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool tried = false;
 };
@@ -51,13 +52,22 @@ static bool load_nccl() {
   LOAD(AllReduce, "ncclAllReduce")
   LOAD(Broadcast, "ncclBroadcast")
   LOAD(CommDestroy, "ncclCommDestroy")
+  LOAD(CommAbort, "ncclCommAbort")
   LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
   return true;
 }
 
+// Fail fast: a rank that hits an NCCL error aborts its communicator, which makes the peers'
+// pending collectives return an error instead of waiting for this rank forever.
 static int nccl_fail(int code, const char *what) {
-  set_error("NCCL error %d (%s) in %s", code, g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "?", what);
+  set_error("NCCL error %d (%s) in %s; communicator aborted", code,
+            g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "?", what);
+  if (g_comm && g_nccl.CommAbort) {
+    ncclComm_t c = g_comm;
+    g_comm = nullptr;
+    g_nccl.CommAbort(c);
+  }
   return SK_ERR_NCCL;
 }
 #define SK_NCCL(expr)                                  \
@@ -122,6 +132,25 @@ int sk_nccl_allreduce(float *buf, size_t count, int on_comm_stream) {
   return SK_OK;
 }
 
+int sk_nccl_allreduce_on(float *buf, size_t count, int stream_id) {
+  SK_REQUIRE(g_comm != nullptr, "sk_nccl_allreduce_on: call sk_nccl_init first");
+  cudaStream_t s = stream_by_id(stream_id);
+  SK_REQUIRE(s != nullptr, "sk_nccl_allreduce_on: unknown stream id %d", stream_id);
+  if (count == 0) return SK_OK;
+  SK_NCCL(g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, g_comm, s));
+  note_launch();
+  return SK_OK;
+}
+
+int sk_nccl_abort(void) {
+  if (g_comm && g_nccl.CommAbort) {
+    ncclComm_t c = g_comm;
+    g_comm = nullptr;
+    g_nccl.CommAbort(c);
+  }
+  return SK_OK;
+}
+
 int sk_nccl_broadcast(float *buf, size_t count, int root) {
   SK_REQUIRE(g_comm != nullptr, "sk_nccl_broadcast: call sk_nccl_init first");
   if (count == 0) return SK_OK;
@@ -140,6 +169,7 @@ int sk_nccl_wait(void) {
 int sk_nccl_destroy(void) {
   if (g_comm) {
     cudaStreamSynchronize(ctx().comm_stream);
+    cudaStreamSynchronize(ctx().opt_stream);
     cudaStreamSynchronize(ctx().stream);
     g_nccl.CommDestroy(g_comm);
     g_comm = nullptr;

@@ -20,7 +20,8 @@ static int parse_2d(const sk_array *a, const sk_array *b, const sk_array *out, G
              (long long)g.K, (long long)b->shape[b->ndim - 2]);
   SK_REQUIRE(out->shape[out->ndim - 2] == g.M && out->shape[out->ndim - 1] == g.N,
              "matmul: output shape mismatch");
-  SK_REQUIRE(out->dtype == SK_F32, "matmul: output must be float32");
+  SK_REQUIRE(out->dtype == SK_F32 || (out->dtype == SK_F64 && a->dtype == SK_F64 && b->dtype == SK_F64),
+             "matmul: output must be float32 (or float64 for float64 operands)");
   SK_REQUIRE(out->strides[out->ndim - 1] == 1 || g.N == 1, "matmul: output rows must be contiguous");
   g.sa_m = a->strides[a->ndim - 2];
   g.sa_k = a->strides[a->ndim - 1];
@@ -101,7 +102,13 @@ static int run_one(const GemmProblem &g0, int algo) {
     }
     return launch_gemm_tc(g, SK_MM_BF16);
   }
-  SK_REQUIRE(g.a_dtype == SK_F32 && g.b_dtype == SK_F32, "matmul: operands must be float32 (or bf16)");
+  if (g.a_dtype == SK_F64 || g.b_dtype == SK_F64) {
+    // float64 operands (np.matmul of float64 / integer Tensors, forward.pyx:172-178): CUDA-core DFMA
+    SK_REQUIRE(g.a_dtype == SK_F64 && g.b_dtype == SK_F64, "matmul: mixed float64 / float32 operands");
+    SK_REQUIRE(g.epilogue == SK_EPI_NONE, "matmul(float64): no fused epilogue");
+    return launch_gemm_f64(g);
+  }
+  SK_REQUIRE(g.a_dtype == SK_F32 && g.b_dtype == SK_F32, "matmul: operands must be float32, float64 or bf16");
   if (algo == SK_MM_AUTO) {
     // SOKET_B200_FP32_GEMM = f16x3 (default) | tf32x3 selects the fp32-parity tensor-core scheme
     static const bool want_f16x3 = !(getenv("SOKET_B200_FP32_GEMM") && !strcmp(getenv("SOKET_B200_FP32_GEMM"), "tf32x3"));
@@ -176,7 +183,7 @@ static int matmul_impl(const sk_array *a, const sk_array *b, const sk_array *bia
     GemmProblem gi = g;
     gi.a = (const char *)g.a + oa * esz_a;
     gi.b = (const char *)g.b + ob * esz_b;
-    gi.c = g.c + oc;
+    gi.c = (float *)((char *)g.c + oc * dtype_size(out->dtype));
     if ((rc = run_one(gi, algo))) return rc;
   }
   return SK_OK;

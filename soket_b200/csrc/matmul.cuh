@@ -28,6 +28,8 @@ struct MMArgs {
 };
 
 int launch_gemm_simt(const MMArgs &p);
+// float64 operands and result (g.a, g.b, g.c point at doubles; strides in elements)
+int launch_gemm_f64(const GemmProblem &g);
 
 // tcgen05 path (matmul_tc.cu)
 bool tc_supported(const GemmProblem &g, int algo);

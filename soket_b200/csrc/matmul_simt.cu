@@ -224,4 +224,40 @@ int launch_gemm_simt(const MMArgs &p) {
   return SK_OK;
 }
 
+// ------------------------------------------------------------------ float64
+// np.matmul on float64 (and, through the host's cast, integer) Tensors: off the training path, so a
+// plain 16 x 16 shared-memory tiled DFMA kernel; any strides, one collapsed batch dimension.
+__global__ void __launch_bounds__(256) gemm_f64_kernel(const double *__restrict__ a, const double *__restrict__ b,
+                                                       double *__restrict__ c, int64_t M, int64_t N, int64_t K,
+                                                       int64_t sa_m, int64_t sa_k, int64_t sb_k, int64_t sb_n,
+                                                       int64_t ldc, int64_t sa_b, int64_t sb_b, int64_t sc_b) {
+  __shared__ double As[16][17], Bs[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t bz = blockIdx.z;
+  const double *A = a + bz * sa_b;
+  const double *B = b + bz * sb_b;
+  const int64_t m = (int64_t)blockIdx.y * 16 + ty, n = (int64_t)blockIdx.x * 16 + tx;
+  double acc = 0.0;
+  for (int64_t k0 = 0; k0 < K; k0 += 16) {
+    As[ty][tx] = (m < M && k0 + tx < K) ? A[m * sa_m + (k0 + tx) * sa_k] : 0.0;
+    Bs[ty][tx] = (k0 + ty < K && n < N) ? B[(k0 + ty) * sb_k + n * sb_n] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fma(As[ty][k], Bs[k][tx], acc);
+    __syncthreads();
+  }
+  if (m < M && n < N) c[bz * sc_b + m * ldc + n] = acc;
+}
+
+int launch_gemm_f64(const GemmProblem &g) {
+  if (g.M == 0 || g.N == 0 || g.batch == 0) return SK_OK;
+  SK_REQUIRE(g.batch <= 65535 && (g.M + 15) / 16 <= 65535, "matmul(float64): problem too large for the DFMA kernel");
+  dim3 grid((unsigned)((g.N + 15) / 16), (unsigned)((g.M + 15) / 16), (unsigned)g.batch);
+  ProfScope ps(SK_PROF_GEMM_SIMT, 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch);
+  gemm_f64_kernel<<<grid, 256, 0, stream()>>>((const double *)g.a, (const double *)g.b, (double *)g.c, g.M, g.N, g.K,
+                                              g.sa_m, g.sa_k, g.sb_k, g.sb_n, g.ldc, g.sa_b, g.sb_b, g.sc_b);
+  SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
 }  // namespace sk

@@ -942,7 +942,7 @@ __device__ __forceinline__ int64_t load_label(const void *p, int dt, int64_t i) 
 __global__ void __launch_bounds__(kNT)
 softmax_ce_kernel(const float *__restrict__ logits, const void *__restrict__ labels, int label_dt,
                   float *__restrict__ row_loss, float *__restrict__ dlogits, int64_t R, int C,
-                  float inv_b) {
+                  float inv_b, unsigned int *__restrict__ dev_err) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (kNT / 32);
   for (int64_t row = (int64_t)blockIdx.x * (kNT / 32) + (threadIdx.x >> 5); row < R; row += warps_total) {
@@ -955,7 +955,11 @@ softmax_ce_kernel(const float *__restrict__ logits, const void *__restrict__ lab
     s = warp_sum(s);
     int64_t y = load_label(labels, label_dt, row);
     if (y < 0) y += C;
-    if (lane == 0 && row_loss) row_loss[row] = (logf(s) + m) - xr[y];
+    // eye(C)[labels] raises IndexError on the reference (device.pyx:239); here the row's loss becomes
+    // NaN, its gradient keeps no one-hot term and the sticky error word makes the next sync raise
+    const bool bad = y < 0 || y >= C;
+    if (bad && lane == 0) atomicOr(dev_err, (unsigned int)SK_DEVERR_LABEL_RANGE);
+    if (lane == 0 && row_loss) row_loss[row] = bad ? __int_as_float(0x7fc00000) : (logf(s) + m) - xr[y];
     if (dlogits) {
       float *dr = dlogits + row * C;
       for (int i = lane; i < C; i += 32) {
@@ -1255,7 +1259,8 @@ int sk_softmax_ce_fwd_bwd(const float *logits, const void *labels, int label_dty
   const float inv_b = (float)(1.0 / (double)rows);
   int grid = grid_for(rows, kNT / 32, 8);
   ProfScope ps(SK_PROF_LOSS, (double)rows * classes * (dlogits ? 8.0 : 4.0));
-  softmax_ce_kernel<<<grid, kNT, 0, stream()>>>(logits, labels, label_dtype, rl, dlogits, rows, (int)classes, inv_b);
+  softmax_ce_kernel<<<grid, kNT, 0, stream()>>>(logits, labels, label_dtype, rl, dlogits, rows, (int)classes, inv_b,
+                                                dev_error_ptr());
   SK_LAUNCH_CHECK();
   if (loss) {
     if ((rc = reduce_rows_f32(SK_RED_MEAN, rl, rows, loss, 1, rows))) return rc;

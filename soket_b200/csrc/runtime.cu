@@ -145,18 +145,43 @@ static cudaEvent_t prof_event() {
 bool prof_on() { return g_prof_on; }
 void prof_begin(int family) {
   cudaEvent_t e = prof_event();
-  cudaEventRecord(e, ctx().stream);
+  cudaEventRecord(e, ctx().launch);
   g_prof_open[family] = e;
 }
 void prof_end(int family, double work) {
   cudaEvent_t e = prof_event();
-  cudaEventRecord(e, ctx().stream);
+  cudaEventRecord(e, ctx().launch);
   g_prof[family].push_back({g_prof_open[family], e, work});
 }
 
 static uint64_t *g_epoch_dev = nullptr;
 const uint64_t *rng_epoch_ptr() { return g_epoch_dev; }
 __global__ void epoch_advance_kernel(uint64_t *e) { *e += 1; }
+
+cudaStream_t stream_by_id(int id) {
+  Context &c = ctx();
+  switch (id) {
+    case SK_STREAM_COMPUTE: return c.stream;
+    case SK_STREAM_COMM: return c.comm_stream;
+    case SK_STREAM_COPY: return c.copy_stream;
+    case SK_STREAM_OPT: return c.opt_stream;
+    default: return nullptr;
+  }
+}
+
+static volatile unsigned int *g_deverr_host = nullptr;
+static unsigned int *g_deverr_dev = nullptr;
+unsigned int *dev_error_ptr() { return g_deverr_dev; }
+int check_dev_error() {
+  if (!g_deverr_host || *g_deverr_host == 0) return SK_OK;
+  const unsigned int w = *g_deverr_host;
+  *g_deverr_host = 0;
+  if (w & SK_DEVERR_LABEL_RANGE)
+    set_error("softmax cross-entropy: a target label is outside [-classes, classes) (index out of bounds)");
+  else
+    set_error("a kernel reported an out-of-range index (code %u)", w);
+  return SK_ERR_INDEX;
+}
 
 static void *g_flush_buf = nullptr;
 static size_t g_flush_bytes = 0;
@@ -210,8 +235,17 @@ int sk_init(int device) {
   SK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   SK_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
   SK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  SK_CUDA(cudaStreamCreateWithFlags(&c.opt_stream, cudaStreamNonBlocking));
+  c.launch = c.stream;
   SK_CUDA(cudaMalloc((void **)&g_epoch_dev, sizeof(uint64_t)));
   SK_CUDA(cudaMemset(g_epoch_dev, 0, sizeof(uint64_t)));
+  {
+    void *h = nullptr;
+    SK_CUDA(cudaHostAlloc(&h, sizeof(unsigned int), cudaHostAllocMapped));
+    g_deverr_host = (volatile unsigned int *)h;
+    *g_deverr_host = 0;
+    SK_CUDA(cudaHostGetDevicePointer((void **)&g_deverr_dev, h, 0));
+  }
   c.device = device;
   c.ready = true;
   return SK_OK;
@@ -230,6 +264,28 @@ int sk_sync(void) {
   SK_CUDA(cudaStreamSynchronize(ctx().stream));
   SK_CUDA(cudaStreamSynchronize(ctx().comm_stream));
   SK_CUDA(cudaStreamSynchronize(ctx().copy_stream));
+  SK_CUDA(cudaStreamSynchronize(ctx().opt_stream));
+  return check_dev_error();
+}
+
+int sk_launch_stream(int stream_id) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  cudaStream_t s = stream_by_id(stream_id);
+  SK_REQUIRE(s != nullptr, "sk_launch_stream: unknown stream id %d", stream_id);
+  ctx().launch = s;
+  return SK_OK;
+}
+int sk_event_record_on(void *ev, int stream_id) {
+  cudaStream_t s = stream_by_id(stream_id);
+  SK_REQUIRE(ev && s, "sk_event_record_on: null event or unknown stream id %d", stream_id);
+  SK_CUDA(cudaEventRecord((cudaEvent_t)ev, s));
+  return SK_OK;
+}
+int sk_stream_wait_event(int stream_id, void *ev) {
+  cudaStream_t s = stream_by_id(stream_id);
+  SK_REQUIRE(ev && s, "sk_stream_wait_event: null event or unknown stream id %d", stream_id);
+  SK_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)ev, 0));
   return SK_OK;
 }
 
@@ -318,7 +374,7 @@ int sk_d2h(void *dst, const void *src, size_t nbytes) {
   if (nbytes == 0) return SK_OK;
   SK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx().stream));
   SK_CUDA(cudaStreamSynchronize(ctx().stream));
-  return SK_OK;
+  return check_dev_error();
 }
 int sk_h2d_async(void *dst, const void *src, size_t nbytes) {
   int rc = ensure_init();
@@ -390,7 +446,7 @@ int sk_event_record(void *ev) {
 }
 int sk_event_sync(void *ev) {
   SK_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
-  return SK_OK;
+  return check_dev_error();
 }
 int sk_event_elapsed_ms(void *start, void *stop, float *ms) {
   SK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));

@@ -3,9 +3,28 @@
 New relative to the reference (no collective, no notion of rank: SURVEY.md
 section 2 / 8e).  The batch is sharded by contiguous row blocks, parameters and
 optimiser state are replicated, and the ONLY collective is an NCCL
-all-reduce(sum) of every trainable parameter's gradient, issued on a dedicated
-comm stream the moment autodiff finalises that gradient, so it overlaps the rest
-of backward; 1/W is folded into the optimiser kernel (`grad_scale`).
+all-reduce(sum) of the gradients; 1/W is folded into the optimiser kernel
+(`grad_scale`).
+
+How a step runs at W > 1:
+
+  * all gradients live in ONE flat fp32 arena, laid out in REVERSE parameter order
+    (the order backward finalises them).  Each parameter's slot is handed to the
+    fused backward kernels (`Tensor._grad_buf`): the dW GEMM, the bias-gradient
+    reduction and the LayerNorm parameter reductions write straight into it, so
+    there is no gather copy (a gradient produced elsewhere is copied in).
+  * the arena is cut into contiguous BUCKETS (~64 MiB, i.e. about one Linear layer
+    each).  The moment autodiff has finalised the last gradient of a bucket, one
+    `ncclAllReduce` over that bucket's range is queued on the comm stream (after an
+    event on the compute stream), and the optimizer update of exactly those
+    parameters is queued on the optimizer stream behind the all-reduce's event --
+    both overlap the rest of backward, which keeps the compute stream.
+  * `step()` flushes whatever is still pending, advances the optimizer's per-step
+    state and makes the compute stream wait for the optimizer stream.
+
+Updating a layer's parameters while backward is still running is safe: every kernel
+that reads them in this step (the layer's own forward and backward) was queued on the
+compute stream before the event its bucket waits for.
 
 Rendezvous: ranks come from the environment torchrun sets (RANK, LOCAL_RANK,
 WORLD_SIZE, MASTER_ADDR, MASTER_PORT).  `torch.distributed` is used for exactly
@@ -16,7 +35,7 @@ through it and it is not on the device path.
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 
 @dataclass
@@ -71,10 +90,13 @@ class Rendezvous:
         while int(self.store.add(key, 0)) < self.env.world:
             time.sleep(0.0005)
 
-    def all_gather_float(self, value: float) -> list[float]:
+    def all_gather_str(self, value: str) -> list[str]:
         self._n += 1
-        self.store.set(f"ag/{self._n}/{self.env.rank}", repr(float(value)))
-        return [float(self.store.get(f"ag/{self._n}/{r}").decode()) for r in range(self.env.world)]
+        self.store.set(f"ag/{self._n}/{self.env.rank}", value)
+        return [self.store.get(f"ag/{self._n}/{r}").decode() for r in range(self.env.world)]
+
+    def all_gather_float(self, value: float) -> list[float]:
+        return [float(v) for v in self.all_gather_str(repr(float(value)))]
 
 
 def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:
@@ -83,57 +105,170 @@ def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:
     return rdv.broadcast_bytes(uid, "nccl_uid")
 
 
+SLOT_ALIGN = 64           # floats: every slot starts on a 256-byte boundary (vector loads, TMA-free GEMM epilogue)
+
+
+def plan_arena(sizes, bucket_floats):
+    """Layout of the flat gradient arena for parameters of `sizes` elements (in parameter-list
+    order).  Slots are placed in REVERSE order -- backward reaches the last layer first -- each
+    aligned to SLOT_ALIGN floats, and cut greedily into buckets of at least `bucket_floats` floats.
+    Returns (offsets, total, buckets) with offsets[i] the slot of parameter i and
+    buckets = [(start, end, [parameter indices in slot order])].  Pure host logic (CPU-tested)."""
+    offsets = [0] * len(sizes)
+    buckets = []
+    off, start, members = 0, 0, []
+    for i in reversed(range(len(sizes))):
+        offsets[i] = off
+        off += (int(sizes[i]) + SLOT_ALIGN - 1) // SLOT_ALIGN * SLOT_ALIGN
+        members.append(i)
+        if off - start >= bucket_floats:
+            buckets.append((start, off, members))
+            start, members = off, []
+    if members:
+        buckets.append((start, off, members))
+    return offsets, off, buckets
+
+
+@dataclass
+class _Bucket:
+    start: int
+    end: int
+    members: list
+    view: object = None
+    ev_ready: object = None
+    ev_reduced: object = None
+    arrived: int = 0
+    launched: bool = False
+    seen: set = field(default_factory=set)
+
+
 class DataParallel:
-    """Gradient all-reduce driver around a soket_b200 model + optimiser.
+    """Bucketed gradient all-reduce + per-bucket optimizer update around a soket_b200 optimiser.
 
-        dp = DataParallel(optim, rdv)       # after sk.init(local_rank)
+        ddp = DataParallel(optim, rdv)      # after sk.init(local_rank)
         ...
-        loss.backward()                     # all-reduces fire per finalised leaf grad
-        dp.finish()                         # compute stream waits for the comm stream
-        optim.step()                        # grad_scale = 1/W inside the fused kernel
-    """
+        loss.backward()                     # buckets are reduced and applied as they complete
+        ddp.step()                          # flush, advance the optimizer, join the streams
 
-    def __init__(self, optim, rdv: Rendezvous | None, overlap: bool = True):
+    At world size 1 `step()` is `optim.step()`.  While a DataParallel object is open the gradients
+    of the optimizer's parameters live in its arena: `p.grad` of one step is overwritten by the
+    next backward, and after `step()` it holds the SUM over ranks (the 1/W is applied inside the
+    optimizer kernel)."""
+
+    def __init__(self, optim, rdv: Rendezvous | None, overlap: bool = True, bucket_mb: float | None = None):
+        from soket_b200 import _core as B
         from soket_b200 import _fused as F
         from soket_b200 import engine as E
-        self.F, self.E = F, E
+        self.B, self.F, self.E = B, F, E
         self.optim = optim
         self.world = 1 if rdv is None else rdv.env.world
         self.overlap = overlap
-        self._ids = {id(p) for p in optim._params}
-        if self.world > 1:
-            uid = exchange_unique_id(rdv, F.nccl_unique_id)
-            F.nccl_init(rdv.env.rank, rdv.env.world, uid)
-            optim.grad_scale = 1.0 / self.world
-            E.set_leaf_grad_hook(self._on_leaf_grad)
+        self._closed = False
+        if self.world == 1:
+            return
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("SOKET_B200_DP_BUCKET_MB", "64"))
+        params = optim._params
+        for p in params:
+            if str(p._data.dtype) != "float32":
+                raise TypeError("data-parallel training supports float32 parameters only "
+                                f"(got {p._data.dtype} of shape {p.shape})")
+            if not p._data.is_contiguous:
+                p._data = B.ascontiguousarray(p._data)
+        uid = exchange_unique_id(rdv, F.nccl_unique_id)
+        F.nccl_init(rdv.env.rank, rdv.env.world, uid)
+        optim.grad_scale = 1.0 / self.world
+        offsets, total, buckets = plan_arena([int(p.size) for p in params], int(bucket_mb * (1 << 20) / 4))
+        self.arena = B.zeros((max(total, 1),), "float32")      # padding between slots stays zero
+        self._slots = []
+        for p, off in zip(params, offsets):
+            slot = self.arena[off:off + int(p.size)].reshape(p.shape)
+            self._slots.append(slot)
+            p._grad_buf = slot
+        self._buckets = []
+        self._where = {}
+        for start, end, members in buckets:
+            b = _Bucket(start, end, members, self.arena[start:end], B.Event(), B.Event())
+            for i in members:
+                self._where[id(params[i])] = (len(self._buckets), i)
+            self._buckets.append(b)
+        self._ev_done = B.Event()
+        E.set_leaf_grad_hook(self._on_leaf_grad)
 
+    # ------------------------------------------------------------------------------------------
     def broadcast_parameters(self, root: int = 0):
         """Identical initial weights on every rank (section 8d config 5)."""
         if self.world == 1:
             return
-        from soket_b200 import _core as B
         for p in self.optim._params:
-            if str(p._data.dtype) != "float32":
-                continue
-            if not p._data.is_contiguous:
-                p._data = B.ascontiguousarray(p._data)
             self.F.nccl_broadcast(p._data, root)
 
     def _on_leaf_grad(self, t):
-        if id(t) not in self._ids:
+        ent = self._where.get(id(t))
+        if ent is None:
             return
+        bi, i = ent
+        slot = self._slots[i]
         g = t._grad._data
-        if not g.is_contiguous:
-            from soket_b200 import _core as B
-            g = B.ascontiguousarray(g)
-            t._grad._data = g
-        self.F.nccl_allreduce(g, self.overlap)
+        if g.data_ptr != slot.data_ptr:
+            # produced outside the fused backward kernels (or summed from several partials)
+            slot[...] = g if g.shape == slot.shape else g.reshape(slot.shape)
+            t._grad._data = slot
+        b = self._buckets[bi]
+        if i not in b.seen:
+            b.seen.add(i)
+            b.arrived += 1
+        if self.overlap and not b.launched and b.arrived == len(b.members):
+            self._launch(b)
+
+    def _launch(self, b):
+        """Queue the bucket's all-reduce (comm stream) and its optimizer update (optimizer stream)."""
+        B = self.B
+        b.ev_ready.record(B.STREAM_COMPUTE)
+        b.ev_ready.wait(B.STREAM_COMM)               # the gradients of this bucket are complete
+        self.F.nccl_allreduce_on(b.view, B.STREAM_COMM)
+        b.ev_reduced.record(B.STREAM_COMM)
+        b.ev_reduced.wait(B.STREAM_OPT)
+        B.launch_stream(B.STREAM_OPT)
+        try:
+            self.optim.update(sorted(b.seen))
+        finally:
+            B.launch_stream(B.STREAM_COMPUTE)
+        b.launched = True
+
+    def step(self):
+        """The optimizer step of a data-parallel iteration (call after `backward()`)."""
+        if self.world == 1:
+            self.optim.step()
+            return
+        B = self.B
+        for b in self._buckets:
+            if not b.launched and b.arrived:
+                self._launch(b)
+        B.launch_stream(B.STREAM_OPT)
+        try:
+            self.optim.end_step()
+        finally:
+            B.launch_stream(B.STREAM_COMPUTE)
+        self._ev_done.record(B.STREAM_OPT)
+        self._ev_done.wait(B.STREAM_COMPUTE)         # the next forward reads the updated parameters
+        for b in self._buckets:
+            b.arrived, b.launched = 0, False
+            b.seen.clear()
 
     def finish(self):
-        if self.world > 1 and self.overlap:
-            self.F.nccl_wait()
+        """Kept for callers of the round-1 API (`finish(); optim.step()`): reduce whatever is
+        pending WITHOUT applying it; the caller's `optim.step()` then updates on the compute stream."""
+        if self.world == 1:
+            return
+        raise RuntimeError("DataParallel.finish() was replaced by DataParallel.step(), which also runs the "
+                           "optimizer (per bucket, overlapped with backward)")
 
     def close(self):
-        if self.world > 1:
+        if self.world > 1 and not self._closed:
+            self._closed = True
             self.E.set_leaf_grad_hook(None)
+            for p in self.optim._params:
+                p._grad_buf = None
+            self.B.synchronize()
             self.F.nccl_destroy()

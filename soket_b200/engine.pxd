@@ -15,3 +15,5 @@ cdef class Tensor:
     cdef public int _pending
     cdef public int _visit
     cdef public int _state
+    cdef public int _nedges        # partial adjoints this node receives in the running backward
+    cdef public object _grad_buf   # ndarray | None: where a fused backward writes this leaf's gradient

@@ -22,11 +22,12 @@ The fused ops used by ``soket_b200.nn`` (linear+bias+relu, layer/batch norm
 (+relu)(+residual), softmax-CE, dropout) are defined at the bottom.
 """
 from libc.stdint cimport int64_t
+from cpython.ref cimport PyObject
 
 import numpy as np
 
 from soket_b200._abi cimport *
-from soket_b200._core cimport ndarray, _new_array, _check, _fptr, _as_device
+from soket_b200._core cimport ndarray, Buffer, _new_array, _check, _fptr, _as_device
 from soket_b200 import _core as B
 from soket_b200 import _fused as F
 
@@ -558,6 +559,7 @@ cdef class Tensor:
         self._inputs = ()
         self._partials = None
         self._retain_grad = False
+        self._grad_buf = None
         self._device = _default_device() if device is None else device
         if isinstance(array, Tensor):
             other = <Tensor> array
@@ -595,6 +597,7 @@ cdef class Tensor:
         t._partials = None
         t._requires_grad = requires_grad
         t._retain_grad = False
+        t._grad_buf = None
         return t
 
     @staticmethod
@@ -883,6 +886,7 @@ cdef inline void _touch(Tensor t, int ep):
         t._visit = ep
         t._state = 0
         t._pending = 0
+        t._nedges = 0
         t._partials = []
 
 
@@ -917,17 +921,29 @@ cdef list _topo(Tensor root):
                 continue
             _touch(i, ep)
             i._pending += 1
+            i._nedges += 1
             if i._state == 0:
                 stack.append((i, False))
     return order
 
 
-cdef object _sum_partials(list parts):
-    """autodiff.pyx:30-41 _sum_nodes, but in place: the first OWNED partial becomes the
-    accumulator; aliased partials are never written to."""
+cdef inline bint _sole_view(object a):
+    """True when `a` is the only array object over its allocation: every view holds a reference to
+    the shared Buffer, so a count of one means no other gradient, retained adjoint or forward value
+    can observe a write through `a`."""
+    cdef Buffer b = (<ndarray> a)._buf      # this local holds one reference itself
+    return (<PyObject *> b).ob_refcnt == 2
+
+
+cdef tuple _sum_partials(list parts):
+    """autodiff.pyx:30-41 _sum_nodes, but in place.  Returns (sum, owned).  A partial is written to
+    only when it was handed to this node alone (the flag set where it was produced) AND no other
+    array shares its storage (`_sole_view`: reshape / transpose / broadcast backward return views
+    of the adjoint they were given, add / sub backward hand the same adjoint to both inputs)."""
     cdef object acc, p
     cdef bint owned, o
     acc, owned = parts[0]
+    owned = owned and _sole_view(acc)
     for k in range(1, len(parts)):
         p, o = parts[k]
         if (acc.shape == p.shape and str(acc.dtype) == 'float32' and str(p.dtype) == 'float32'
@@ -935,18 +951,17 @@ cdef object _sum_partials(list parts):
             if owned:
                 F.accumulate_(acc, p)
                 continue
-            if o:
+            if o and _sole_view(p):
                 F.accumulate_(p, acc)
                 acc = p; owned = True
                 continue
         acc = B.add(acc, p)
         owned = True
-    return acc
+    return acc, owned
 
 
 cdef void _finalize_leaf(Tensor n):
-    g = _sum_partials(n._partials)
-    g = _unbroadcast(g, n.shape)
+    g = _unbroadcast(_sum_partials(n._partials)[0], n.shape)
     n._partials = None
     # overwritten, never accumulated (autodiff.pyx:221-222).  The dtype TAG is the tensor's own: every
     # backward fn wraps its result with the input's dtype (backward.pyx:14-24), whatever the data is (Q11)
@@ -971,10 +986,19 @@ cdef void _compute_gradient(Tensor root, object seed):
                 else:
                     n._partials = None
             continue
-        g = _sum_partials(n._partials)
-        g = _unbroadcast(g, n.shape)
+        g0, g_owned = _sum_partials(n._partials)
+        g = _unbroadcast(g0, n.shape)
+        if g is not g0:
+            g_owned = True                   # a fresh reduction
+        g0 = None
         n._partials = None
         grads = n._op.bwd(n, g)
+        # who receives what: an array handed to several inputs (add / sub backward, add_relu) or kept
+        # as this node's retained gradient must not be accumulated into by any of them
+        nrecv = {}
+        for x, gi in zip(n._inputs, grads):
+            if x is not None and gi is not None and (<Tensor> x)._requires_grad:
+                nrecv[id(gi)] = nrecv.get(id(gi), 0) + 1
         for x, gi in zip(n._inputs, grads):
             if x is None:
                 continue
@@ -983,10 +1007,12 @@ cdef void _compute_gradient(Tensor root, object seed):
                 continue
             i._pending -= 1
             if gi is not None:
-                i._partials.append((gi, gi is not g))
+                o = nrecv[id(gi)] == 1 and (gi is not g or (g_owned and not n._retain_grad))
+                i._partials.append((gi, o))
             if i._pending == 0 and i._op is None and len(i._partials):
                 _finalize_leaf(i)
         n._grad = Tensor._const(g, n._dtype, False) if n._retain_grad else None
+        g = None; grads = None
 
 
 # ============================================================================ creation fns
@@ -1089,6 +1115,14 @@ def logsumexp(Tensor x, *axes, keepdims=False):
 
 
 # ============================================================================ fused ops
+cdef inline object _slot(object t):
+    """The gradient-arena slot of a LEAF parameter (or None).  Only leaves: a non-leaf's adjoint may
+    be consumed by reference, and a slot is rewritten on the next backward."""
+    if t is None or (<Tensor> t)._op is not None or (<Tensor> t)._nedges != 1:
+        return None      # a parameter with several consumers gets its partials summed into a fresh array
+    return (<Tensor> t)._grad_buf
+
+
 class _LinearOp(Op):
     """relu?(X @ W + b) in one GEMM launch (prototypes.pyx:108-115 + :302).  Backward:
     dZ = relu mask * adj (one pass), dX = dZ @ W.T, dW = X.T @ dZ (both on .T views,
@@ -1107,10 +1141,11 @@ class _LinearOp(Op):
         gx = None
         want_b = b is not None and b.requires_grad
         if x.requires_grad and w.requires_grad:
+            # _grad_buf: a data-parallel gradient-arena slot the result is written to directly
             if want_b:     # one split of adj shared by both GEMMs, its column sums = the bias gradient
-                gx, gw, gb = B.linear_bwd(a2, x2, w._data, True)
+                gx, gw, gb = B.linear_bwd(a2, x2, w._data, True, _slot(w), _slot(b))
             else:
-                gx, gw = B.linear_bwd(a2, x2, w._data)
+                gx, gw = B.linear_bwd(a2, x2, w._data, False, _slot(w))
                 gb = None
             if x._data.ndim != 2:
                 gx = B.reshape(gx, x.shape)
@@ -1162,7 +1197,7 @@ class _LayerNormOp(Op):
             want_p = (g is not None and g.requires_grad) or (b is not None and b.requires_grad)
             dx, dg, db = F.layernorm_dropout_bwd(
                 adj, x._data, None if g is None else g._data, None if b is None else b._data,
-                self.mean, self.rstd, self.relu, keep, 1.0 / keep, seed, want_p)
+                self.mean, self.rstd, self.relu, keep, 1.0 / keep, seed, want_p, _slot(g), _slot(b))
             return (dg, db, dx if x.requires_grad else None, None)
         mode = 0
         if self.relu:
@@ -1172,7 +1207,7 @@ class _LayerNormOp(Op):
         dx, dg, db, dres = F.layernorm_bwd(
             adj, x._data, None if g is None else g._data, None if b is None else b._data,
             self.mean, self.rstd, node._data if mode == 2 else None, mode,
-            want_res and mode == 2, want_p)
+            want_res and mode == 2, want_p, _slot(g), _slot(b))
         if want_res and mode != 2:
             dres = adj    # plain residual add: the adjoint passes through (aliased)
         return (dg, db, dx if x.requires_grad else None, dres if want_res else None)

@@ -26,16 +26,27 @@ cdef class Optimizer:
         self.grad_scale = 1.0
 
     def step(self):
+        """One optimizer step over every parameter (soket/optim.pyx `step`)."""
+        self.update(None)
+        self.end_step()
+
+    def update(self, subset=None):
+        """Update the parameters at the given positions of the parameter list (all when None) with the
+        CURRENT step's hyper-parameters.  Data-parallel training calls it once per gradient bucket,
+        as each bucket's all-reduce lands, then `end_step()` once."""
         raise NotImplementedError()
 
-    cdef tuple _live(self):
+    def end_step(self):
+        """Advance per-step state (Adam's bias corrections)."""
+
+    cdef tuple _live(self, subset=None):
         """Parameters that received a gradient (optim.pyx:100-102 skips the rest);
         anything the multi-tensor kernel cannot take goes to the slow list."""
         cdef list ps = [], gs = [], idx = []
         cdef Tensor p, g
-        cdef int i = 0
-        for x in self._params:
-            p = <Tensor> x
+        cdef int i
+        for i in (range(len(self._params)) if subset is None else subset):
+            p = <Tensor> self._params[i]
             if p._grad is not None:
                 g = <Tensor> p._grad
                 if not g._data.is_contiguous:
@@ -43,7 +54,6 @@ cdef class Optimizer:
                 if not p._data.is_contiguous:
                     p._data = B.ascontiguousarray(p._data)
                 ps.append(p._data); gs.append(g._data); idx.append(i)
-            i += 1
         return ps, gs, idx
 
 
@@ -65,8 +75,8 @@ cdef class SGD(Optimizer):
         if dampening != 0.0 and self._have_momentum:
             raise NotImplementedError('soket_b200.optim.SGD: dampening != 0 is not supported')
 
-    def step(self):
-        ps, gs, idx = self._live()
+    def update(self, subset=None):
+        ps, gs, idx = self._live(subset)
         if not ps:
             return
         lr = -self._lr if self._maximize else self._lr      # optim.pyx:127-131: p - lr * (-g)
@@ -110,12 +120,12 @@ cdef class Adam(Optimizer):
         if self._capturable:
             self._bias_dev = B.array(np.array([self._beta1_t, self._beta2_t], dtype=np.float64))
 
-    def step(self):
+    def update(self, subset=None):
         if B.is_capturing() and not self._capturable:
             raise RuntimeError("Adam.step inside a CUDA-graph capture: the bias corrections 1 - beta^t are host "
                                "scalars (optim.pyx:191-195) and would be frozen in the graph; construct the "
                                "optimizer with Adam(..., capturable=True) or capture SGD steps only")
-        ps, gs, idx = self._live()
+        ps, gs, idx = self._live(subset)
         # first-step parameters (no state yet) and the rest go to separate launches:
         # optim.pyx:224-238 initialises m, v without the beta * 0 term
         fresh = [k for k, i in enumerate(idx) if self._u[i] is None]
@@ -137,6 +147,8 @@ cdef class Adam(Optimizer):
                         self._lr, self._beta1, self._beta2, self._eps, wd,
                         self._one_minus_beta1_t, self._one_minus_beta2_t, first, self.grad_scale,
                         self._bias_dev)
+
+    def end_step(self):
         if self._capturable:
             # the device copy is what the kernels read; the host mirrors below only follow the
             # steps issued through this method (graph replays advance the device copy alone)

@@ -80,6 +80,19 @@ CASES = [
     ("reuse_of_a_node", [(4, 4)], lambda s, a: (a * a + a) * a - a.sum(0)),
     ("diamond", [(3, 4), (4,)], lambda s, a, b: ((a + b) * (a - b)).sum(1) + (a * b).mean(1)),
     ("stack_no_grad", [(3, 4), (3, 4)], lambda s, a, b: s.stack([a, b], axis=1)),
+    # ---- adjoint aliasing: add / sub backward hand the SAME adjoint to both inputs and reshape /
+    # transpose / same-shape sum backward return VIEWS of it; an input with a second consumer must not
+    # accumulate into storage another gradient still reads (autodiff.pyx:30-41, backward.pyx:60-86)
+    ("alias_reshape_add_multi_consumer", [(2, 3), (6,)],
+        lambda s, x, w: ((x.reshape(6) + w) * 3.0).sum() + (x * 2.0).sum()),
+    ("alias_transpose_add_multi_consumer", [(3, 4), (4, 3)],
+        lambda s, a, b: (a.T + b) * 2.0 + (a * a).T),
+    ("alias_sub_permute_multi_consumer", [(2, 3, 4), (4, 2, 3)],
+        lambda s, a, b: (b - a.permute(2, 0, 1)) * 1.5 + (a * 0.5).permute(2, 0, 1) + b * b),
+    ("alias_same_shape_sum_multi_consumer", [(1, 4), (1, 4)],
+        lambda s, a, b: (a.sum(0, keepdims=True) + b) * 3.0 + a * 2.0),
+    ("alias_add_both_inputs_reused", [(3, 4), (3, 4)],
+        lambda s, a, b: (a + b) * (a - b) + (a + b) + a * 2.0 + b * 3.0),
 ]
 
 # forward-only cases: integer / bool results, never differentiable (tensor.pyx:812-920, 2050-2338)
@@ -164,7 +177,24 @@ def _creation(s, a):
             s.rand(3, 4) * 0.0, s.randn(2, 2, dtype=s.float64) * 0.0, s.randb(5, p=1.0), s.randb(2, 3, p=0.0)]
 
 
+def _matmul_dtypes(s, a):
+    """np.matmul's result dtype follows the promoted Tensor dtype (forward.pyx:172-178): float64 and
+    integer operands keep their precision / type instead of being computed in float32."""
+    rng = np.random.default_rng(7)
+    f64a, f64b = rng.standard_normal((5, 7)), rng.standard_normal((7, 3))
+    big = np.array([[2 ** 20 + 1, 3], [5, 2 ** 21 + 7]], "int64")
+    out = [_t(s, f64a) @ _t(s, f64b),
+           _t(s, f64a.astype("float32")) @ _t(s, f64b),
+           _t(s, _ints((4, 6), "int32", 1)) @ _t(s, _ints((6, 2), "int32", 2)),
+           _t(s, big) @ _t(s, big),
+           _t(s, _ints((4, 6), "int32", 3)) @ _t(s, f64b[:6].astype("float32")),
+           _t(s, _ints((2, 3, 4), "int16", 4).astype("float64")) @ _t(s, f64a[:4]),
+           _t(s, f64a).T @ _t(s, f64a)]
+    return [_try(lambda o=o: o) for o in out]
+
+
 MULTI_CASES = [
+    ("matmul_dtypes", _matmul_dtypes),
     ("mixed_add", _mixed(lambda x, y: x + y)),
     ("mixed_sub", _mixed(lambda x, y: x - y)),
     ("mixed_mul", _mixed(lambda x, y: x * y)),

@@ -12,12 +12,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("norm,opt", [("layer", "sgd"), ("batch", "sgd"), ("layer", "adam")])
-def test_two_rank_training_matches_shard_emulation(sk, norm, opt):
+@pytest.mark.parametrize("norm,opt,wide", [("layer", "sgd", 0), ("batch", "sgd", 0), ("layer", "adam", 0),
+                                           ("layer", "sgd", 1), ("layer", "adam", 1)])
+def test_two_rank_training_matches_shard_emulation(sk, norm, opt, wide):
     if sk.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt)
-    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam")
+    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt, DP_WIDE=str(wide))
+    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam") + 7 * wide
     r = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", str(port),

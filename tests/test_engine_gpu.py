@@ -250,3 +250,48 @@ def test_tensor_ops_and_quirks(sk):
     want = np.zeros((3, 4), "float32"); want[1:, ::2] = 1
     assert np.array_equal(s.grad.numpy(), want)
     assert soket.Tensor(np.array([[1, 5, 2]], "float32")).argmax(-1).numpy().tolist() == [1]
+
+
+def test_add_relu_hands_one_adjoint_to_two_inputs(sk):
+    """add_relu backward gives the SAME array to both inputs: an input with a second consumer must
+    not accumulate into it (it is also the other input's gradient), nor into a retained one."""
+    import soket_b200.api as soket
+    from soket_b200 import engine as E
+    rng = np.random.default_rng(4)
+    an, bn, wn = (rng.standard_normal((6, 8)).astype("float32") for _ in range(3))
+    a, b = soket.Tensor(an, requires_grad=True), soket.Tensor(bn, requires_grad=True)
+    out = E.add_relu(a, b)
+    ((out * soket.Tensor(wn)).sum() + (a * 2.0).sum()).backward()
+    mask = ((an + bn) > 0).astype("float32")
+    assert np.allclose(b.grad.numpy(), mask * wn, rtol=1e-6, atol=1e-7)
+    assert np.allclose(a.grad.numpy(), mask * wn + 2.0, rtol=1e-6, atol=1e-7)
+    # the Residual fallback shape: add_relu(x, inner(x)) with the inner value's gradient retained
+    x = soket.Tensor(an, requires_grad=True)
+    inner = x * 0.5
+    inner.retain_grad()
+    out = E.add_relu(x, inner)
+    (out * soket.Tensor(wn)).sum().backward()
+    mask = ((an + 0.5 * an) > 0).astype("float32")
+    assert np.allclose(inner.grad.numpy(), mask * wn, rtol=1e-6, atol=1e-7)
+    assert np.allclose(x.grad.numpy(), 1.5 * mask * wn, rtol=1e-6, atol=1e-7)
+
+
+def test_softmax_ce_rejects_labels_outside_the_classes(sk):
+    """eye(C)[labels] raises IndexError on the reference (device.pyx:239); the fused kernel reports
+    it through the sticky device error word at the next sync point and stays usable."""
+    import soket_b200.api as soket
+    from soket_b200 import nn
+    rng = np.random.default_rng(5)
+    logits = soket.Tensor(rng.standard_normal((4, 10)).astype("float32"), requires_grad=True)
+    crit = nn.SoftmaxCrossEntropyLoss()
+    loss = crit(logits, soket.Tensor(np.array([1, 255, 3, 2], "uint8")))
+    with pytest.raises(IndexError):
+        loss.item()
+    loss = crit(logits, soket.Tensor(np.array([1, -12, 3, 2], "int32")))
+    with pytest.raises(IndexError):
+        sk.synchronize()
+    good = crit(logits, soket.Tensor(np.array([1, -1, 3, 2], "int32")))     # -1 = last class, as NumPy
+    x = logits.numpy().astype(np.float64)
+    lse = np.log(np.exp(x - x.max(1, keepdims=True)).sum(1)) + x.max(1)
+    want = (lse - x[np.arange(4), [1, 9, 3, 2]]).mean()
+    assert abs(good.item() - want) <= 1e-5 * abs(want)

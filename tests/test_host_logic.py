@@ -118,3 +118,32 @@ def test_public_api_covers_the_reference(ref_soket):
     assert int(mine.DeviceType.GPU) == int(ref_soket.DeviceType.GPU) and mine.gpu().type == mine.DeviceType.GPU
     with mine.lazy():
         pass
+
+
+def test_gradient_arena_plan_reverse_order_aligned_buckets():
+    """soket_b200.dp.plan_arena (host logic of the data-parallel gradient arena, SURVEY.md section 8e:
+    "bucketed in reverse layer order"): slots in reverse parameter order, 256-byte aligned,
+    non-overlapping, buckets contiguous and covering every parameter exactly once."""
+    from soket_b200.dp import SLOT_ALIGN, plan_arena
+    sizes = [784 * 4096, 4096] + [4096 * 4096, 4096, 4096, 4096] * 4 + [4096 * 10, 10]
+    offsets, total, buckets = plan_arena(sizes, 16 << 20)
+    order = sorted(range(len(sizes)), key=lambda i: offsets[i])
+    assert order == list(reversed(range(len(sizes))))            # backward reaches the last layer first
+    end = 0
+    for i in order:
+        assert offsets[i] % SLOT_ALIGN == 0 and offsets[i] >= end
+        end = offsets[i] + sizes[i]
+    assert total >= end and total % SLOT_ALIGN == 0
+    seen = []
+    pos = 0
+    for start, stop, members in buckets:
+        assert start == pos and stop > start
+        pos = stop
+        for i in members:
+            assert start <= offsets[i] and offsets[i] + sizes[i] <= stop
+        seen += members
+    assert pos == total and sorted(seen) == list(range(len(sizes)))
+    assert all(stop - start >= (16 << 20) for start, stop, _ in buckets[:-1])
+    # degenerate inputs
+    assert plan_arena([], 1024) == ([], 0, [])
+    assert plan_arena([5], 1 << 30) == ([0], SLOT_ALIGN, [(0, SLOT_ALIGN, [0])])

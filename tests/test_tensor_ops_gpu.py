@@ -121,5 +121,8 @@ def test_dtype_semantics_and_creation_match_reference(sk, case):
         got = got.astype(want.dtype)
         if want.dtype.kind in "biu":
             assert np.array_equal(got, want), (name, i, got, want)
+        elif want.dtype == np.float64 and name == "matmul_dtypes":
+            # float64 operands are multiplied in float64, not silently in float32
+            assert np.allclose(got, want, rtol=1e-12, atol=1e-13), (name, i, got, want)
         else:
             assert np.allclose(got, want, rtol=1e-5, atol=1e-7, equal_nan=True), (name, i, got, want)
