@@ -245,6 +245,30 @@ int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo);
 /* fused Linear(+ReLU): out = epi(x @ w + bias). bias may be NULL for EPI_NONE/RELU */
 int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
                   sk_array *out, int epilogue, int algo);
+/* Pre-split operands of the fp16x3 GEMM.  The fp32-parity matmul (`_MATMUL`, forward.pyx:172-178) runs on
+ * tcgen05 as three fp16 MMAs over X * scale = hi + lo; sk_matmul / sk_linear_* split their operands inside
+ * every call.  A training step uses each matrix in several GEMMs (a layer's input in forward and in
+ * dW = X.T @ adj, backward.pyx:734; its weight in forward and in dX = adj @ W.T, backward.pyx:722; the
+ * adjoint in dX and dW), so the resident path splits each ONCE, with one power-of-two scale for the
+ * whole matrix -- which is what lets the same hi / lo pair be consumed K-major by one GEMM and
+ * MN-major by another -- or has the producing kernel emit the split (sk_layernorm_*_ex).
+ *   scale4: device float[4] = {scale, 1/scale, |max| (or the bound the scale came from), 0}. */
+typedef struct {
+  const void *hi, *lo;   /* fp16, identical layout: stored rows of `ld` elements (ld % 8 == 0) */
+  int64_t ld;
+  int mn_major;          /* 0: a stored row is one M (A) / N (B) index with K contiguous; 1: a stored row is one K */
+  const float *scale;    /* the matrix's scale4 */
+} sk_split_operand;
+/* x (rows, cols) pitch ldx -> hi, lo (pitch ldh = cols rounded up to 8, padding zero) + scale4.  amax_bits:
+ * device word with the bit pattern of max |x| or of an upper bound (NULL: computed by an extra pass).
+ * colsum_out (or NULL): the column sums of x from the same pass (the bias gradient, autodiff.pyx:84). */
+int sk_split_f16(const float *x, int64_t rows, int64_t cols, int64_t ldx, const unsigned int *amax_bits, void *hi,
+                 void *lo, int64_t ldh, float *scale4, float *colsum_out);
+/* c (M, N) pitch ldc = epi(A @ B [+ c if accumulate]) with A = M x K, B = K x N given as split operands.
+ * Needs M >= 256, N >= 128, K >= 64 (sk_gemm_f16x3_supported).  epilogue: sk_mm_epilogue. */
+int sk_gemm_f16x3_supported(int64_t M, int64_t N, int64_t K);
+int sk_gemm_f16x3(const sk_split_operand *a, const sk_split_operand *b, float *c, int64_t ldc, int64_t M, int64_t N,
+                  int64_t K, const float *bias, int epilogue, int accumulate);
 /* Linear backward (backward.pyx:704-742 for y = x @ w): dx (B,I) = adj (B,O) @ w(I,O).T and
  * dw (I,O) = x(B,I).T @ adj in one call, so that the fp16x3 path splits adj once for both
  * GEMMs; falls back to two sk_matmul calls on .T views for other shapes / layouts. */
@@ -258,6 +282,20 @@ int sk_cast_bf16(const sk_array *src, sk_array *dst);
 
 /* ------------------------------------------------------------ fused nn kernels
  * replaces the op SEQUENCES of forward.pyx:224-353 / backward.pyx:959-1132. */
+/* Optional by-products of the LayerNorm kernels for the fp16x3 GEMM that consumes their result (the
+ * Linear that follows a LayerNorm(+ReLU)(+Dropout) or residual LayerNorm in model.py:24-37; the Linear
+ * backward that consumes a LayerNorm backward's dx).  Used by the *_ex entry points; NULL = none.
+ *   forward : split_hi / split_lo (fp16, rows x cols, cols % 8 == 0) + split_scale (device float[4])
+ *             receive the OUTPUT as X * scale = hi + lo.  The scale is chosen before any element exists,
+ *             from |gamma * norm + beta| <= max|gamma| sqrt(cols) + max|beta| (+ the residual's bound
+ *             residual_scale[2], x 1/keep under dropout) -- no extra pass, no second kernel.
+ *   backward: dx_absmax (device word, zeroed by the caller) receives the bit pattern of max |dx|. */
+typedef struct {
+  void *split_hi, *split_lo;
+  float *split_scale;
+  const float *residual_scale;
+  unsigned int *dx_absmax;
+} sk_ln_extras;
 /* LayerNorm over the last axis of a contiguous (rows, cols) fp32 matrix.
  * y = gamma * ((x-mean) * rstd) + beta ; biased variance ; saves mean/rstd.
  * relu != 0 fuses the following ReLU; residual != NULL fuses
@@ -265,6 +303,9 @@ int sk_cast_bf16(const sk_array *src, sk_array *dst);
 int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta,
                      const float *residual, float *y, float *mean, float *rstd,
                      int64_t rows, int64_t cols, float eps, int relu);
+int sk_layernorm_fwd_ex(const float *x, const float *gamma, const float *beta, const float *residual,
+                        float *y, float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                        int relu, const sk_ln_extras *extras);
 /* dX, dgamma, dbeta (per-group partials column-reduced internally).
  * mask_mode: 0 none; 1 the LN output fed a ReLU directly: the mask (LN(x) > 0)
  * is recomputed from x/mean/rstd/gamma/beta, nothing extra is read; 2 the mask
@@ -275,6 +316,10 @@ int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const
                      const float *mean, const float *rstd, const float *y_out, int mask_mode,
                      float *dx, float *dgamma, float *dbeta, float *dresidual,
                      int64_t rows, int64_t cols);
+int sk_layernorm_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                        const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                        float *dx, float *dgamma, float *dbeta, float *dresidual, int64_t rows,
+                        int64_t cols, const sk_ln_extras *extras);
 /* LayerNorm (+ReLU) followed by Dropout in ONE pass each way (the Linear - LayerNorm - ReLU -
  * Dropout run of the residual block, model.py:24-31; prototypes.pyx:746-760 for the dropout):
  * y = (relu(LN(x)) * mask) * (1/keep), mask ~ Bernoulli(keep) identified by *seed (the same draw
@@ -284,10 +329,17 @@ int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const
 int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y,
                              float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
                              int relu, float keep, uint64_t *seed);
+int sk_layernorm_dropout_fwd_ex(const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                                float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
+                                uint64_t *seed_out, const sk_ln_extras *extras);
 int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
                              const float *mean, const float *rstd, int relu, float keep, float r_keep,
                              uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
                              int64_t cols);
+int sk_layernorm_dropout_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                                const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                                uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                                int64_t cols, const sk_ln_extras *extras);
 /* BatchNorm1d over axis 0 of a contiguous (rows, cols) fp32 matrix, training
  * mode (always: quirk Q4, forward.pyx:281), biased variance, running stats
  * rm = (1-m) rm + m mean (forward.pyx:308-318). */

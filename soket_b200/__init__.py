@@ -43,6 +43,8 @@ from ._core import (  # noqa: F401,E402
     memory_stats, empty_cache, version, Event, Graph, PinnedBuffer,
     arena_create, arena_begin, arena_end, arena_destroy, rng_epoch_advance, is_capturing, prefetch_wait,
     profile_enable, profile_reset, profile_collect,
+    SplitMat, split_f16, get_split, gemm_split, gemm_split_supported,
+    launch_stream, STREAM_COMPUTE, STREAM_COMM, STREAM_COPY, STREAM_OPT,
 )
 
 __version__ = "0.1.0"

@@ -137,6 +137,37 @@ cdef extern from "soket_b200.h" nogil:
     int sk_matmul(const sk_array *a, const sk_array *b, sk_array *out, int algo)
     int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias,
                       sk_array *out, int epilogue, int algo)
+    ctypedef struct sk_split_operand:
+        const void *hi
+        const void *lo
+        int64_t ld
+        int mn_major
+        const float *scale
+    int sk_split_f16(const float *x, int64_t rows, int64_t cols, int64_t ldx, const unsigned int *amax_bits,
+                     void *hi, void *lo, int64_t ldh, float *scale4, float *colsum_out)
+    int sk_gemm_f16x3_supported(int64_t M, int64_t N, int64_t K)
+    int sk_gemm_f16x3(const sk_split_operand *a, const sk_split_operand *b, float *c, int64_t ldc, int64_t M,
+                      int64_t N, int64_t K, const float *bias, int epilogue, int accumulate)
+    ctypedef struct sk_ln_extras:
+        void *split_hi
+        void *split_lo
+        float *split_scale
+        const float *residual_scale
+        unsigned int *dx_absmax
+    int sk_layernorm_fwd_ex(const float *x, const float *gamma, const float *beta, const float *residual,
+                            float *y, float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                            int relu, const sk_ln_extras *extras)
+    int sk_layernorm_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                            const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                            float *dx, float *dgamma, float *dbeta, float *dresidual, int64_t rows,
+                            int64_t cols, const sk_ln_extras *extras)
+    int sk_layernorm_dropout_fwd_ex(const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                                    float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
+                                    uint64_t *seed_out, const sk_ln_extras *extras)
+    int sk_layernorm_dropout_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                                    const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                                    uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                                    int64_t cols, const sk_ln_extras *extras)
     int sk_linear_bwd(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw)
     int sk_cast_bf16(const sk_array *src, sk_array *dst)
     int sk_linear_bwd_bias(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw, float *db)

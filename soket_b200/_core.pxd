@@ -6,6 +6,7 @@ from soket_b200._abi cimport sk_array
 cdef class Buffer:
     cdef size_t ptr
     cdef size_t nbytes
+    cdef long version           # bumped by every in-place write through any view (see ndarray._touch)
 
 
 cdef class ndarray:
@@ -17,6 +18,7 @@ cdef class ndarray:
     cdef int64_t _strides[8]    # element strides
     cdef object _np_dtype       # numpy dtype object (host metadata)
     cdef bint _readonly
+    cdef public object _meta    # derived data valid for one Buffer.version: SplitMat | AbsMax | None
 
     cdef int64_t _numel(self)
     cdef bint _is_contiguous(self)
@@ -24,9 +26,36 @@ cdef class ndarray:
     cdef int _desc_bcast(self, sk_array *d, int ndim, const int64_t *shape) except -1
     cdef ndarray _view(self, int ndim, const int64_t *shape, const int64_t *strides, int64_t offset)
     cdef ndarray _compact(self)
+    cdef void _touch(self)
+
+
+cdef class SplitMat:
+    """A float32 matrix as the fp16x3 GEMM consumes it: X * scale = hi + lo, one scale (sk_split_f16)."""
+    cdef public ndarray hi
+    cdef public ndarray lo
+    cdef public ndarray scale   # float32 (4,): {scale, 1/scale, |max| or bound, 0}
+    cdef public int64_t rows
+    cdef public int64_t cols
+    cdef public int64_t ld
+    cdef size_t src_ptr
+    cdef long version
+    cdef long epoch
+    cdef long capture
+    cdef bint valid_for(self, ndarray x)
+
+
+cdef class AbsMax:
+    """Device word with the bit pattern of max |x| of the array it is attached to."""
+    cdef public ndarray word
+    cdef long version
+    cdef long epoch
+    cdef long capture
 
 
 cdef ndarray _new_array(int ndim, const int64_t *shape, int code)
+cdef SplitMat _new_split(int64_t rows, int64_t cols)
+cdef void _bind_split(SplitMat m, ndarray x)
+cdef long _graph_epoch()
 cdef ndarray _as_device(object x)
 cdef int _check(int rc) except -1
 cdef float *_fptr(ndarray a) except NULL

@@ -96,6 +96,7 @@ cdef class Buffer:
     def __cinit__(self):
         self.ptr = 0
         self.nbytes = 0
+        self.version = 0
 
     def __dealloc__(self):
         if self.ptr != 0:
@@ -179,6 +180,16 @@ cdef class ndarray:
         self._ndim = 0
         self._code = SK_F32
         self._readonly = False
+        self._meta = None
+
+    cdef void _touch(self):
+        """The contents were (or are about to be) overwritten in place: everything derived from the
+        old contents -- an operand split, a known |max| -- is stale, through every view."""
+        self._buf.version += 1
+        self._meta = None
+
+    def mark_modified(self):
+        self._touch()
 
     # ---- C-level helpers ------------------------------------------------------
     cdef int64_t _numel(self):
@@ -359,6 +370,7 @@ cdef class ndarray:
         return argmin(self, axis, out, keepdims=keepdims)
 
     def fill(self, value):
+        self._touch()
         _fill(self, value)
 
     def __getitem__(self, idx):
@@ -858,6 +870,7 @@ cdef int _setitem(ndarray a, object idx, object value) except -1:
     cdef ndarray view = <ndarray> target
     cdef ndarray src
     cdef sk_array s, d
+    a._touch()
     if isinstance(value, (bool, int, float)):
         _fill(view, value)
         return 0
@@ -1325,6 +1338,7 @@ def linear_bwd(adj, x, w, bint want_bias=False, out_dw=None, out_db=None):
     cdef ndarray dw
     if out_dw is not None:
         dw = <ndarray> out_dw
+        dw._touch()
         if dw._code != SK_F32 or dw._ndim != 2 or dw._shape[0] != shp[0] or dw._shape[1] != shp[1] or not dw._is_contiguous():
             raise ValueError('linear_bwd: out_dw must be a contiguous float32 array of w\'s shape')
     else:
@@ -1336,6 +1350,7 @@ def linear_bwd(adj, x, w, bint want_bias=False, out_dw=None, out_db=None):
         shp[0] = a._shape[1]
         if out_db is not None:
             db = <ndarray> out_db
+            db._touch()
             if db._code != SK_F32 or db._numel() != shp[0] or not db._is_contiguous():
                 raise ValueError('linear_bwd: out_db must be a contiguous float32 vector of length O')
         else:
@@ -1344,6 +1359,172 @@ def linear_bwd(adj, x, w, bint want_bias=False, out_dw=None, out_db=None):
         return dx, dw, db
     _check(sk_linear_bwd(&da, &dxx, &dww, &ddx, &ddw))
     return dx, dw
+
+
+# --------------------------------------------------------------------------- pre-split GEMM operands
+# (sk_split_f16 / sk_gemm_f16x3: include/soket_b200.h, "Pre-split operands of the fp16x3 GEMM")
+cdef long _GRAPH_EPOCH = 0      # bumped by every graph replay (buffers rewritten behind the host's back)
+cdef long _CAPTURE_ID = 0       # bumped by every Graph.begin()
+
+
+cdef long _graph_epoch():
+    return _GRAPH_EPOCH
+
+
+cdef inline long _capture_now():
+    """0 in eager mode, else the id of the running capture.  Derived data made DURING a capture exists
+    only inside that graph (its kernels have not run): it may feed later nodes of the same capture,
+    never eager code; data made eagerly may feed a capture (its buffers are real)."""
+    return _CAPTURE_ID if sk_graph_capturing() else 0
+
+
+cdef class SplitMat:
+    cdef bint valid_for(self, ndarray x):
+        """Still describes the CURRENT contents of x?  (No in-place write through any view since the
+        split, no graph replay, same storage and shape; never during a capture, where the kernels
+        that would have filled it have not run.)"""
+        return (self.src_ptr == x._ptr and self.version == x._buf.version and self.epoch == _GRAPH_EPOCH
+                and x._ndim == 2 and x._shape[0] == self.rows and x._shape[1] == self.cols
+                and (self.capture == 0 or self.capture == _capture_now()))
+
+    def __repr__(self):
+        return f'SplitMat({self.rows} x {self.cols}, ld {self.ld})'
+
+
+cdef class AbsMax:
+    pass
+
+
+cdef SplitMat _new_split(int64_t rows, int64_t cols):
+    cdef SplitMat m = SplitMat.__new__(SplitMat)
+    cdef int64_t shp[2]
+    m.rows = rows; m.cols = cols
+    m.ld = (cols + 7) // 8 * 8
+    shp[0] = rows; shp[1] = m.ld
+    m.hi = _new_array(2, shp, SK_F16)
+    m.lo = _new_array(2, shp, SK_F16)
+    shp[0] = 4
+    m.scale = _new_array(1, shp, SK_F32)
+    m.src_ptr = 0; m.version = -1; m.epoch = -1; m.capture = 0
+    return m
+
+
+cdef void _bind_split(SplitMat m, ndarray x):
+    """m holds the split of x's current contents: remember that on x (until x is written to)."""
+    m.src_ptr = x._ptr
+    m.version = x._buf.version
+    m.epoch = _GRAPH_EPOCH
+    m.capture = _capture_now()
+    x._meta = m
+
+
+def new_absmax_word(ndarray owner=None):
+    """A zeroed device word for a kernel to atomicMax |x| bit patterns into (sk_ln_extras.dx_absmax)."""
+    cdef AbsMax a = AbsMax.__new__(AbsMax)
+    cdef int64_t one = 1
+    a.word = _new_array(1, &one, SK_U32)
+    _check(sk_memset(<void *> a.word._ptr, 0, 4))
+    a.version = -1; a.epoch = -1; a.capture = 0
+    return a
+
+
+def bind_absmax(AbsMax a, ndarray x):
+    a.version = x._buf.version
+    a.epoch = _GRAPH_EPOCH
+    a.capture = _capture_now()
+    x._meta = a
+
+
+def split_f16(x, want_colsum=False, out_colsum=None):
+    """float32 (rows, cols) -> SplitMat (and the column sums of x when asked: the bias gradient rides
+    along with the adjoint's split, autodiff.pyx:84).  Uses the |max| a producing kernel attached to
+    x (AbsMax) when there is one, else computes it in an extra pass."""
+    cdef ndarray a = _as_device(x)
+    if a._ndim != 2 or a._code != SK_F32:
+        raise TypeError('split_f16: expected a 2-D float32 array')
+    a = a._compact()
+    cdef SplitMat m = _new_split(a._shape[0], a._shape[1])
+    cdef const unsigned int *amax = NULL
+    cdef AbsMax am
+    if isinstance(a._meta, AbsMax):
+        am = <AbsMax> a._meta
+        if (am.version == a._buf.version and am.epoch == _GRAPH_EPOCH
+                and (am.capture == 0 or am.capture == _capture_now())):
+            amax = <const unsigned int *> am.word._ptr
+    cdef ndarray cs = None
+    cdef int64_t cols = a._shape[1]
+    if want_colsum:
+        if out_colsum is not None:
+            cs = <ndarray> out_colsum
+            if cs._code != SK_F32 or cs._numel() != cols or not cs._is_contiguous():
+                raise ValueError('split_f16: out_colsum must be a contiguous float32 vector of `cols` elements')
+            cs._touch()
+        else:
+            cs = _new_array(1, &cols, SK_F32)
+    _check(sk_split_f16(<const float *> a._ptr, a._shape[0], a._shape[1], a._strides[0] if a._shape[0] > 1 else a._shape[1],
+                        amax, <void *> m.hi._ptr, <void *> m.lo._ptr, m.ld, <float *> m.scale._ptr,
+                        <float *> cs._ptr if cs is not None else NULL))
+    _bind_split(m, a)
+    if want_colsum:
+        return m, cs
+    return m
+
+
+def get_split(x):
+    """The SplitMat of x: the one a producing kernel (or an earlier call) attached to it if x has not
+    been written to since, else a fresh split."""
+    cdef ndarray a = <ndarray> x
+    if isinstance(a._meta, SplitMat) and (<SplitMat> a._meta).valid_for(a):
+        return a._meta
+    return split_f16(a)
+
+
+def gemm_split_supported(int64_t M, int64_t N, int64_t K):
+    return bool(sk_gemm_f16x3_supported(M, N, K))
+
+
+def gemm_split(SplitMat a, bint a_trans, SplitMat b, bint b_trans, bias=None, bint relu=False, out=None,
+               bint accumulate=False):
+    """epi(op(A) @ op(B) [+ out]) on the tcgen05 fp16x3 kernel from pre-split operands.  A is the
+    matrix `a` (a.rows x a.cols) or, with a_trans, its transpose -- the SAME hi / lo arrays, consumed
+    MN-major instead of K-major; likewise B.  Returns `out` (M, N) float32."""
+    cdef int64_t M = a.cols if a_trans else a.rows
+    cdef int64_t K = a.rows if a_trans else a.cols
+    cdef int64_t Kb = b.cols if b_trans else b.rows
+    cdef int64_t N = b.rows if b_trans else b.cols
+    if K != Kb:
+        raise ValueError(f'gemm_split: inner dimensions differ ({K} vs {Kb})')
+    cdef sk_split_operand oa, ob
+    oa.hi = <const void *> a.hi._ptr; oa.lo = <const void *> a.lo._ptr; oa.ld = a.ld
+    oa.mn_major = 1 if a_trans else 0            # A stored (M, K): K-major; stored (K, M): MN-major
+    oa.scale = <const float *> a.scale._ptr
+    ob.hi = <const void *> b.hi._ptr; ob.lo = <const void *> b.lo._ptr; ob.ld = b.ld
+    ob.mn_major = 0 if b_trans else 1            # B stored (K, N): MN-major; stored (N, K): K-major
+    ob.scale = <const float *> b.scale._ptr
+    cdef int64_t shp[2]
+    cdef ndarray c
+    if out is not None:
+        c = <ndarray> out
+        if c._code != SK_F32 or c._ndim != 2 or c._shape[0] != M or c._shape[1] != N or not c._is_contiguous():
+            raise ValueError('gemm_split: out must be a contiguous float32 (M, N) array')
+        c._touch()
+    else:
+        if accumulate:
+            raise ValueError('gemm_split: accumulate needs out')
+        shp[0] = M; shp[1] = N
+        c = _new_array(2, shp, SK_F32)
+    cdef ndarray bi = None
+    cdef int epi
+    if bias is not None:
+        bi = _as_device(bias)._compact()
+        if bi._code != SK_F32 or bi._numel() != N:
+            raise ValueError('gemm_split: bias must be a float32 vector of N elements')
+        epi = SK_EPI_BIAS_RELU if relu else SK_EPI_BIAS
+    else:
+        epi = SK_EPI_RELU if relu else SK_EPI_NONE
+    _check(sk_gemm_f16x3(&oa, &ob, <float *> c._ptr, N, M, N, K, <const float *> bi._ptr if bi is not None else NULL,
+                         epi, accumulate))
+    return c
 
 
 # --------------------------------------------------------------------------- random
@@ -1589,6 +1770,8 @@ cdef class Graph:
             sk_graph_destroy(self._exec)
 
     def begin(self):
+        global _CAPTURE_ID
+        _CAPTURE_ID += 1
         _check(sk_graph_begin())
 
     def end(self):
@@ -1599,8 +1782,10 @@ cdef class Graph:
         self._keep.append(obj)
 
     def launch(self):
+        global _GRAPH_EPOCH
         if self._exec == NULL:
             raise RuntimeError('graph has not been captured')
+        _GRAPH_EPOCH += 1          # a replay rewrites buffers behind the host's back: drop derived caches
         _check(sk_graph_launch(self._exec))
 
 
@@ -1636,6 +1821,7 @@ cdef class PinnedBuffer:
         """Async H2D on the compute stream."""
         if not dst._is_contiguous() or <size_t> dst.nbytes != self._nbytes:
             raise ValueError('PinnedBuffer.copy_to_device: size / layout mismatch')
+        dst._touch()
         _check(sk_h2d_async(<void *> dst._ptr, self._p, self._nbytes))
 
     def prefetch_to_device(self, ndarray dst):
@@ -1643,6 +1829,7 @@ cdef class PinnedBuffer:
         is queued next; call `prefetch_wait()` before the first kernel that reads `dst`."""
         if not dst._is_contiguous() or <size_t> dst.nbytes != self._nbytes:
             raise ValueError('PinnedBuffer.prefetch_to_device: size / layout mismatch')
+        dst._touch()
         _check(sk_h2d_prefetch(<void *> dst._ptr, self._p, self._nbytes))
 
     def copy_from_device(self, ndarray src):

@@ -14,7 +14,8 @@ from libc.stdint cimport int64_t, uint64_t
 from libc.stdlib cimport malloc, free
 
 from soket_b200._abi cimport *
-from soket_b200._core cimport ndarray, _new_array, _check, _fptr, _as_device
+from soket_b200._core cimport ndarray, _new_array, _check, _fptr, _as_device, SplitMat, AbsMax, _new_split, _bind_split
+from soket_b200 import _core as _B
 
 
 cdef inline float *_opt(object a) except? NULL:
@@ -31,14 +32,38 @@ cdef inline int _rows_cols(ndarray x, int64_t *rows, int64_t *cols) except -1:
     return 0
 
 
-def layernorm_fwd(ndarray x, gamma=None, beta=None, residual=None, double eps=1e-5, bint relu=False):
+cdef inline bint _split_worthwhile(int64_t rows, int64_t cols):
+    """Would a Linear consuming a (rows, cols) activation take the pre-split tcgen05 path?"""
+    return rows >= 256 and cols >= 256 and cols % 8 == 0
+
+
+def layernorm_fwd(ndarray x, gamma=None, beta=None, residual=None, double eps=1e-5, bint relu=False,
+                  bint emit_split=False, residual_split=None):
     """y = [relu]( [residual +] gamma * ((x - mean) * rstd) + beta ) over the last axis.
-    Returns (y, mean, rstd); mean/rstd have shape (rows,)."""
+    Returns (y, mean, rstd); mean/rstd have shape (rows,).  emit_split: the kernel also writes y as
+    the fp16 hi / lo pair of the fp16x3 GEMM (attached to y as its SplitMat); with a residual this
+    needs the residual's own SplitMat (for the bound of |residual|)."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
     cdef ndarray y = _new_array(x._ndim, x._shape, SK_F32)
     cdef ndarray mean = _new_array(1, &rows, SK_F32)
     cdef ndarray rstd = _new_array(1, &rows, SK_F32)
+    cdef sk_ln_extras ex
+    cdef SplitMat m = None
+    cdef SplitMat rm
+    if emit_split and x._ndim == 2 and _split_worthwhile(rows, cols) and (residual is None or residual_split is not None):
+        m = _new_split(rows, cols)
+        ex.split_hi = <void *> m.hi._ptr; ex.split_lo = <void *> m.lo._ptr
+        ex.split_scale = <float *> m.scale._ptr
+        ex.residual_scale = NULL
+        ex.dx_absmax = NULL
+        if residual is not None:
+            rm = <SplitMat> residual_split
+            ex.residual_scale = <const float *> rm.scale._ptr
+        _check(sk_layernorm_fwd_ex(_fptr(x), _opt(gamma), _opt(beta), _opt(residual), _fptr(y),
+                                   _fptr(mean), _fptr(rstd), rows, cols, <float> eps, relu, &ex))
+        _bind_split(m, y)
+        return y, mean, rstd
     _check(sk_layernorm_fwd(_fptr(x), _opt(gamma), _opt(beta), _opt(residual), _fptr(y),
                             _fptr(mean), _fptr(rstd), rows, cols, <float> eps, relu))
     return y, mean, rstd
@@ -53,13 +78,15 @@ cdef inline ndarray _vec_out(object out, int64_t cols):
     o = <ndarray> out
     if o._code != SK_F32 or o._numel() != cols or not o._is_contiguous():
         raise ValueError('expected a contiguous float32 output vector of the parameter\'s length')
+    o._touch()
     return o
 
 
 def layernorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd,
                   y_out=None, int mask_mode=0, bint want_dresidual=False, bint want_params=True,
-                  out_dgamma=None, out_dbeta=None):
-    """Returns (dx, dgamma, dbeta, dresidual)."""
+                  out_dgamma=None, out_dbeta=None, bint emit_absmax=False):
+    """Returns (dx, dgamma, dbeta, dresidual).  emit_absmax: the kernel also leaves max |dx| in a
+    device word attached to dx (AbsMax), which saves the adjoint's split its own |max| pass."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
     cdef ndarray dx = _new_array(x._ndim, x._shape, SK_F32)
@@ -69,20 +96,44 @@ def layernorm_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rst
         db = _vec_out(out_dbeta, cols)
     if want_dresidual:
         dres = _new_array(x._ndim, x._shape, SK_F32)
+    cdef sk_ln_extras ex
+    cdef AbsMax am
+    if emit_absmax and x._ndim == 2 and _split_worthwhile(rows, cols):
+        am = _B.new_absmax_word()
+        ex.split_hi = NULL; ex.split_lo = NULL; ex.split_scale = NULL; ex.residual_scale = NULL
+        ex.dx_absmax = <unsigned int *> am.word._ptr
+        _check(sk_layernorm_bwd_ex(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
+                                   _opt(y_out), mask_mode, _fptr(dx), _opt(dg), _opt(db), _opt(dres),
+                                   rows, cols, &ex))
+        _B.bind_absmax(am, dx)
+        return dx, dg, db, dres
     _check(sk_layernorm_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
                             _opt(y_out), mask_mode, _fptr(dx), _opt(dg), _opt(db), _opt(dres),
                             rows, cols))
     return dx, dg, db, dres
 
 
-def layernorm_dropout_fwd(ndarray x, gamma, beta, double eps, bint relu, double keep):
-    """y = dropout([relu](LN(x))) in one pass.  Returns (y, mean, rstd, seed)."""
+def layernorm_dropout_fwd(ndarray x, gamma, beta, double eps, bint relu, double keep, bint emit_split=False):
+    """y = dropout([relu](LN(x))) in one pass.  Returns (y, mean, rstd, seed); emit_split as in
+    layernorm_fwd."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
     cdef ndarray y = _new_array(x._ndim, x._shape, SK_F32)
     cdef ndarray mean = _new_array(1, &rows, SK_F32)
     cdef ndarray rstd = _new_array(1, &rows, SK_F32)
     cdef uint64_t seed = 0
+    cdef sk_ln_extras ex
+    cdef SplitMat m
+    if emit_split and x._ndim == 2 and _split_worthwhile(rows, cols):
+        m = _new_split(rows, cols)
+        ex.split_hi = <void *> m.hi._ptr; ex.split_lo = <void *> m.lo._ptr
+        ex.split_scale = <float *> m.scale._ptr
+        ex.residual_scale = NULL
+        ex.dx_absmax = NULL
+        _check(sk_layernorm_dropout_fwd_ex(_fptr(x), _opt(gamma), _opt(beta), _fptr(y), _fptr(mean), _fptr(rstd),
+                                           rows, cols, <float> eps, relu, <float> keep, &seed, &ex))
+        _bind_split(m, y)
+        return y, mean, rstd, seed
     _check(sk_layernorm_dropout_fwd(_fptr(x), _opt(gamma), _opt(beta), _fptr(y), _fptr(mean), _fptr(rstd),
                                     rows, cols, <float> eps, relu, <float> keep, &seed))
     return y, mean, rstd, seed
@@ -90,7 +141,7 @@ def layernorm_dropout_fwd(ndarray x, gamma, beta, double eps, bint relu, double 
 
 def layernorm_dropout_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, ndarray rstd, bint relu,
                           double keep, double r_keep, seed, bint want_params=True,
-                          out_dgamma=None, out_dbeta=None):
+                          out_dgamma=None, out_dbeta=None, bint emit_absmax=False):
     """Backward of layernorm_dropout_fwd from the adjoint of its output.  Returns (dx, dgamma, dbeta)."""
     cdef int64_t rows, cols
     _rows_cols(x, &rows, &cols)
@@ -99,6 +150,17 @@ def layernorm_dropout_bwd(ndarray adj, ndarray x, gamma, beta, ndarray mean, nda
     if want_params:
         dg = _vec_out(out_dgamma, cols)
         db = _vec_out(out_dbeta, cols)
+    cdef sk_ln_extras ex
+    cdef AbsMax am
+    if emit_absmax and x._ndim == 2 and _split_worthwhile(rows, cols):
+        am = _B.new_absmax_word()
+        ex.split_hi = NULL; ex.split_lo = NULL; ex.split_scale = NULL; ex.residual_scale = NULL
+        ex.dx_absmax = <unsigned int *> am.word._ptr
+        _check(sk_layernorm_dropout_bwd_ex(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
+                                           relu, <float> keep, <float> r_keep, <uint64_t> seed, _fptr(dx),
+                                           _opt(dg), _opt(db), rows, cols, &ex))
+        _B.bind_absmax(am, dx)
+        return dx, dg, db
     _check(sk_layernorm_dropout_bwd(_fptr(adj), _fptr(x), _opt(gamma), _opt(beta), _fptr(mean), _fptr(rstd),
                                     relu, <float> keep, <float> r_keep, <uint64_t> seed, _fptr(dx),
                                     _opt(dg), _opt(db), rows, cols))
@@ -197,6 +259,7 @@ def accumulate_(ndarray acc, ndarray part):
     """acc += part, in place."""
     if acc._numel() != part._numel():
         raise ValueError('accumulate_: size mismatch')
+    acc._touch()
     _check(sk_accumulate(_fptr(acc), _fptr(part), acc._numel()))
     return acc
 
@@ -233,6 +296,7 @@ def sgd_step(list params, list grads, double lr, double weight_decay=0.0, double
         p = <ndarray> params[i]; g = <ndarray> grads[i]
         if p._numel() != g._numel():
             raise ValueError(f'sgd_step: parameter {i} and its gradient differ in size')
+        p._touch()
         L.p[i] = _fptr(p); L.g[i] = _fptr(g); L.sizes[i] = p._numel()
     _check(sk_sgd_step(n, L.p, L.g, L.sizes, lr, weight_decay, grad_scale))
 
@@ -261,6 +325,7 @@ def adam_step(list params, list grads, list m, list v, double lr, double beta1, 
         p = <ndarray> params[i]; g = <ndarray> grads[i]
         if p._numel() != g._numel():
             raise ValueError(f'adam_step: parameter {i} and its gradient differ in size')
+        p._touch()
         L.p[i] = _fptr(p); L.g[i] = _fptr(g)
         L.m[i] = _fptr(<ndarray> m[i]); L.v[i] = _fptr(<ndarray> v[i])
         L.sizes[i] = p._numel()
@@ -292,11 +357,13 @@ def nccl_init(int rank, int world, bytes uid):
 
 def nccl_allreduce(ndarray buf, bint on_comm_stream=False):
     """In-place sum all-reduce of a contiguous fp32 buffer."""
+    buf._touch()
     _check(sk_nccl_allreduce(_fptr(buf), <size_t> buf._numel(), on_comm_stream))
 
 
 def nccl_allreduce_on(ndarray buf, int stream):
     """In-place sum all-reduce on the given stream id; the caller orders it with events."""
+    buf._touch()
     _check(sk_nccl_allreduce_on(_fptr(buf), <size_t> buf._numel(), stream))
 
 
@@ -305,6 +372,7 @@ def nccl_abort():
 
 
 def nccl_broadcast(ndarray buf, int root=0):
+    buf._touch()
     _check(sk_nccl_broadcast(_fptr(buf), <size_t> buf._numel(), root))
 
 

@@ -4,6 +4,7 @@
 // and the Linear(+ReLU) module sequence prototypes.pyx:108-115,302.
 #include "common.cuh"
 #include "matmul.cuh"
+#include "matmul_split.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -203,6 +204,32 @@ int sk_linear_fwd(const sk_array *x, const sk_array *w, const sk_array *bias, sk
                   int epilogue, int algo) {
   SK_REQUIRE(epilogue >= SK_EPI_NONE && epilogue <= SK_EPI_RELU, "linear: bad epilogue %d", epilogue);
   return matmul_impl(x, w, bias, out, epilogue, algo);
+}
+
+int sk_split_f16(const float *x, int64_t rows, int64_t cols, int64_t ldx, const unsigned int *amax_bits, void *hi,
+                 void *lo, int64_t ldh, float *scale4, float *colsum_out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(x && hi && lo && scale4, "sk_split_f16: null pointer");
+  SK_REQUIRE(rows > 0 && cols > 0, "sk_split_f16: empty matrix");
+  SK_REQUIRE(ldx >= cols && ldh >= cols && ldh % 8 == 0 && ldh == (cols + 7) / 8 * 8,
+             "sk_split_f16: ldh must be cols rounded up to a multiple of 8 (got %lld for %lld columns)",
+             (long long)ldh, (long long)cols);
+  SK_REQUIRE(ldx % 4 == 0 || rows == 1, "sk_split_f16: source pitch must be a multiple of 4 elements");
+  SK_REQUIRE(((((uintptr_t)x) | ((uintptr_t)hi) | ((uintptr_t)lo) | ((uintptr_t)scale4)) & 15) == 0,
+             "sk_split_f16: pointers must be 16-byte aligned");
+  ProfScope pp(SK_PROF_GEMM_PREP, (double)rows * (double)cols * (amax_bits ? 8.0 : 12.0));
+  return split_f16_tensor(x, ldx, rows, cols, (const uint32_t *)amax_bits, (__half *)hi, (__half *)lo, ldh, scale4,
+                          colsum_out);
+}
+
+int sk_gemm_f16x3_supported(int64_t M, int64_t N, int64_t K) { return gemm_f16x3_shape_ok(M, N, K) ? 1 : 0; }
+
+int sk_gemm_f16x3(const sk_split_operand *a, const sk_split_operand *b, float *c, int64_t ldc, int64_t M, int64_t N,
+                  int64_t K, const float *bias, int epilogue, int accumulate) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  return gemm_f16x3_presplit(a, b, c, ldc, M, N, K, bias, epilogue, accumulate);
 }
 
 static int linear_bwd_impl(const sk_array *adj, const sk_array *x, const sk_array *w, sk_array *dx, sk_array *dw,

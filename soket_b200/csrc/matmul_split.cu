@@ -24,17 +24,6 @@ __device__ __forceinline__ float absmax4(float m, const float4 &v) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
 }
 
-// amax -> (scale, 1/scale) as exact powers of two.  Zero / non-finite rows are left alone.
-__device__ __forceinline__ void pow2_scale(float amax, float &scale, float &inv) {
-  const uint32_t bits = __float_as_uint(amax);
-  const int ef = (int)((bits >> 23) & 0xFF);
-  if (ef == 0 || ef == 0xFF) { scale = 1.f; inv = 1.f; return; }
-  int shift = 14 - (ef - 127);
-  if (shift > 126) shift = 126;       // rows below 2^-112: products underflow fp32 anyway
-  scale = __uint_as_float((uint32_t)(shift + 127) << 23);
-  inv = __uint_as_float((uint32_t)(127 - shift) << 23);
-}
-
 struct Half8 { uint4 v; };
 
 __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s, uint4 &hi, uint4 &lo) {
@@ -60,8 +49,17 @@ template <int TPR, int VPT>
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ hi, __half *__restrict__ lo,
                   int64_t ldh, float *__restrict__ inv_scale, int64_t outer, int inner,
-                  float *__restrict__ cs_part) {
+                  float *__restrict__ cs_part, const uint32_t *__restrict__ tensor_amax) {
   __shared__ float red[8];
+  // tensor_amax: ONE scale for the whole matrix, from the bit pattern of (a bound of) its |max|; block 0
+  // publishes {scale, 1/scale, amax, 0} in inv_scale[0..3] instead of one inverse scale per row
+  float ts = 1.f, tinv = 1.f;
+  if (tensor_amax) {
+    pow2_scale(__uint_as_float(*tensor_amax), ts, tinv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      inv_scale[0] = ts; inv_scale[1] = tinv; inv_scale[2] = __uint_as_float(*tensor_amax); inv_scale[3] = 0.f;
+    }
+  }
   constexpr int RPB = 256 / TPR;
   const int t = threadIdx.x % TPR, grp = threadIdx.x / TPR;
   const int units = (int)(ldh >> 3);
@@ -102,18 +100,20 @@ split_rows_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__
         }
       }
     }
-    m = warp_max(m);
-    if (TPR > 32) {
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-      __syncthreads();
-      m = red[0];
+    float s = ts, inv = tinv;
+    if (!tensor_amax) {
+      m = warp_max(m);
+      if (TPR > 32) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        m = red[0];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      }
+      pow2_scale(m, s, inv);
+      if (live && t == 0) inv_scale[row] = inv;
     }
-    float s, inv;
-    pow2_scale(m, s, inv);
-    if (live && t == 0) inv_scale[row] = inv;
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
       const int u = t + j * TPR;
@@ -168,27 +168,37 @@ colsum_partials_kernel(const float *__restrict__ part, int64_t P, int64_t ld, fl
 // second time from L1/L2).
 __global__ void __launch_bounds__(256)
 split_rows_long_kernel(const float *__restrict__ x, int64_t ldx, __half *__restrict__ hi, __half *__restrict__ lo,
-                       int64_t ldh, float *__restrict__ inv_scale, int64_t outer, int64_t inner) {
+                       int64_t ldh, float *__restrict__ inv_scale, int64_t outer, int64_t inner,
+                       const uint32_t *__restrict__ tensor_amax) {
   __shared__ float red[8];
   const int64_t units = ldh >> 3;
+  float ts = 1.f, tinv = 1.f;
+  if (tensor_amax) {
+    pow2_scale(__uint_as_float(*tensor_amax), ts, tinv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      inv_scale[0] = ts; inv_scale[1] = tinv; inv_scale[2] = __uint_as_float(*tensor_amax); inv_scale[3] = 0.f;
+    }
+  }
   for (int64_t row = blockIdx.x; row < outer; row += gridDim.x) {
     const float *xr = x + row * ldx;
-    float m = 0.f;
-    for (int64_t c = (int64_t)threadIdx.x * 4; c < inner; c += 1024) {
-      if (c + 4 <= inner) m = absmax4(m, *reinterpret_cast<const float4 *>(xr + c));
-      else
-        for (int64_t k = c; k < inner; ++k) m = fmaxf(m, fabsf(xr[k]));
-    }
-    m = warp_max(m);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    m = red[0];
+    float s = ts, inv = tinv;
+    if (!tensor_amax) {
+      float m = 0.f;
+      for (int64_t c = (int64_t)threadIdx.x * 4; c < inner; c += 1024) {
+        if (c + 4 <= inner) m = absmax4(m, *reinterpret_cast<const float4 *>(xr + c));
+        else
+          for (int64_t k = c; k < inner; ++k) m = fmaxf(m, fabsf(xr[k]));
+      }
+      m = warp_max(m);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      m = red[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    float s, inv;
-    pow2_scale(m, s, inv);
-    if (threadIdx.x == 0) inv_scale[row] = inv;
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      pow2_scale(m, s, inv);
+      if (threadIdx.x == 0) inv_scale[row] = inv;
+    }
     for (int64_t u = threadIdx.x; u < units; u += 256) {
       const int64_t c = u * 8;
       float v[8];
@@ -293,6 +303,89 @@ split_cols_kernel(const float *__restrict__ x, int64_t ldx, const float *__restr
 }
 
 // ---------------------------------------------------------------- host side
+// row-major (outer x inner) fp32 -> hi / lo (pitch ldh); per-row scales into inv_scale[outer], or with
+// tensor_amax one scale for the whole matrix into inv_scale[0..3]
+static int launch_split_rows(const float *x, int64_t ldx, int64_t outer, int64_t inner, __half *hi, __half *lo,
+                             int64_t ldh, float *inv_scale, float *colsum_out, const uint32_t *tensor_amax) {
+  int rc;
+  const int64_t units = ldh / 8;
+  float *cs_part = nullptr;
+  int64_t cs_rows = 0;
+  // with column sums: fewer, longer-running blocks keep the partial matrix small (4 per SM)
+#define ROWS(TPR, VPT)                                                                                  \
+  do {                                                                                                  \
+    const int grid = grid_for(outer, 256 / TPR, colsum_out ? 4 : 16);                                   \
+    if (colsum_out) {                                                                                   \
+      cs_rows = (int64_t)grid * (256 / TPR);                                                            \
+      if ((rc = sk_malloc((size_t)(cs_rows * ldh) * sizeof(float), (void **)&cs_part))) return rc;      \
+    }                                                                                                   \
+    split_rows_kernel<TPR, VPT><<<grid, 256, 0, stream()>>>(x, ldx, hi, lo, ldh, inv_scale, outer,      \
+                                                            (int)inner, cs_part, tensor_amax);          \
+  } while (0)
+  if (units <= 32) ROWS(32, 1);
+  else if (units <= 64) ROWS(32, 2);
+  else if (units <= 128) ROWS(32, 4);
+  else if (units <= 256) ROWS(256, 1);
+  else if (units <= 512) ROWS(256, 2);
+  else if (units <= 1024) ROWS(256, 4);
+  else {
+    const int grid = grid_for(outer, 1, 8);
+    split_rows_long_kernel<<<grid, 256, 0, stream()>>>(x, ldx, hi, lo, ldh, inv_scale, outer, inner, tensor_amax);
+  }
+#undef ROWS
+  SK_LAUNCH_CHECK();
+  if (cs_part) {
+    colsum_partials_kernel<<<(unsigned)((ldh / 4 + 7) / 8), 256, 0, stream()>>>(cs_part, cs_rows, ldh, colsum_out, inner);
+    SK_LAUNCH_CHECK();
+    sk_free(cs_part);   // stream-ordered
+  }
+  return SK_OK;
+}
+
+// max |x| over a (rows x cols) matrix as a bit pattern (non-negative floats order like their bits)
+__global__ void __launch_bounds__(256)
+absmax_tensor_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int64_t cols, uint32_t *__restrict__ out) {
+  __shared__ float red[8];
+  float m = 0.f;
+  const int64_t c4 = cols >> 2, n4 = rows * c4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / c4, c = (i - r * c4) * 4;
+    m = absmax4(m, __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c)));   // read again by the split pass
+  }
+  if ((cols & 3) && blockIdx.x == 0)
+    for (int64_t r = threadIdx.x; r < rows; r += 256)
+      for (int64_t c = c4 * 4; c < cols; ++c) m = fmaxf(m, fabsf(x[r * ldx + c]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    if (m > 0.f) atomicMax(out, __float_as_uint(m));
+  }
+}
+
+int split_f16_tensor(const float *x, int64_t ldx, int64_t rows, int64_t cols, const uint32_t *amax_bits, __half *hi,
+                     __half *lo, int64_t ldh, float *scale4, float *colsum_out) {
+  if (colsum_out && !split_colsum_supported(cols)) {
+    set_error("split_f16_tensor: column sums come with rows of up to 8192 elements only");
+    return SK_ERR_ARG;
+  }
+  int rc;
+  uint32_t *own = nullptr;
+  if (!amax_bits) {
+    if ((rc = sk_malloc(sizeof(uint32_t), (void **)&own))) return rc;
+    SK_CUDA(cudaMemsetAsync(own, 0, sizeof(uint32_t), stream()));
+    const int grid = grid_for(rows * (cols >> 2) + 1, 256, 8);
+    absmax_tensor_kernel<<<grid, 256, 0, stream()>>>(x, ldx, rows, cols, own);
+    SK_LAUNCH_CHECK();
+    amax_bits = own;
+  }
+  rc = launch_split_rows(x, ldx, rows, cols, hi, lo, ldh, scale4, colsum_out, amax_bits);
+  if (own) sk_free(own);   // stream-ordered
+  return rc;
+}
+
 void SplitOperand::release() {
   if (hi) sk_free(hi);
   if (inv_scale) sk_free(inv_scale);
@@ -325,36 +418,9 @@ int split_f16(const float *x, int64_t ldx, int64_t outer, int64_t inner, bool sc
   // inverse scales, then (MN-major) the column-max scratch words
   if ((rc = sk_malloc((size_t)n_scale * (scale_rows ? 4 : 8), (void **)&out.inv_scale))) { out.release(); return rc; }
   if (scale_rows) {
-    const int64_t units = ldh / 8;
-    float *cs_part = nullptr;
-    int64_t cs_rows = 0;
-    // with column sums: fewer, longer-running blocks keep the partial matrix small (4 per SM)
-#define ROWS(TPR, VPT)                                                                                  \
-  do {                                                                                                  \
-    const int grid = grid_for(outer, 256 / TPR, colsum_out ? 4 : 16);                                   \
-    if (colsum_out) {                                                                                   \
-      cs_rows = (int64_t)grid * (256 / TPR);                                                            \
-      if ((rc = sk_malloc((size_t)(cs_rows * ldh) * sizeof(float), (void **)&cs_part))) { out.release(); return rc; } \
-    }                                                                                                   \
-    split_rows_kernel<TPR, VPT><<<grid, 256, 0, stream()>>>(x, ldx, out.hi, out.lo, ldh, out.inv_scale, \
-                                                            outer, (int)inner, cs_part);                \
-  } while (0)
-    if (units <= 32) ROWS(32, 1);
-    else if (units <= 64) ROWS(32, 2);
-    else if (units <= 128) ROWS(32, 4);
-    else if (units <= 256) ROWS(256, 1);
-    else if (units <= 512) ROWS(256, 2);
-    else if (units <= 1024) ROWS(256, 4);
-    else {
-      const int grid = grid_for(outer, 1, 8);
-      split_rows_long_kernel<<<grid, 256, 0, stream()>>>(x, ldx, out.hi, out.lo, ldh, out.inv_scale, outer, inner);
-    }
-#undef ROWS
-    SK_LAUNCH_CHECK();
-    if (cs_part) {
-      colsum_partials_kernel<<<(unsigned)((ldh / 4 + 7) / 8), 256, 0, stream()>>>(cs_part, cs_rows, ldh, colsum_out, inner);
-      SK_LAUNCH_CHECK();
-      sk_free(cs_part);   // stream-ordered
+    if ((rc = launch_split_rows(x, ldx, outer, inner, out.hi, out.lo, ldh, out.inv_scale, colsum_out, nullptr))) {
+      out.release();
+      return rc;
     }
   } else {
     uint32_t *colmax = (uint32_t *)(out.inv_scale + n_scale);

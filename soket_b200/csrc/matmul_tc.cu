@@ -410,6 +410,7 @@ static int launch_kind(const GemmProblem &g, const Operand &oa, const Operand &o
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
   p.epilogue = g.epilogue;
   p.row_inv = nullptr; p.col_inv = nullptr;
+  p.a_inv1 = nullptr; p.b_inv1 = nullptr; p.accumulate = 0;
   p.group_m = 1;
   p.sched = nullptr;
   p.tiles_m = (int)((g.M + BM - 1) / BM);
@@ -577,6 +578,41 @@ int linear_bwd_f16x3(const float *adj, const float *x, const float *w, float *dx
   sx.release();
   *done = rc == SK_OK;
   return rc;
+}
+
+// fp16x3 GEMM on operands that were split BEFORE the call (sk_split_f16, or emitted by the kernel that
+// produced the matrix): no operand pass here.  Each operand carries ONE power-of-two scale, so the
+// same hi / lo pair serves as a K-major operand in one GEMM and as an MN-major operand in another
+// (a Linear layer's input X in forward and in dW = X.T @ adj; its weight in forward and in dX).
+bool gemm_f16x3_shape_ok(int64_t M, int64_t N, int64_t K) { return M >= 256 && N >= 128 && K >= 64; }
+
+int gemm_f16x3_presplit(const sk_split_operand *a, const sk_split_operand *b, float *c, int64_t ldc, int64_t M,
+                        int64_t N, int64_t K, const float *bias, int epilogue, int accumulate) {
+  SK_REQUIRE(a && b && c && a->hi && a->lo && b->hi && b->lo && a->scale && b->scale, "sk_gemm_f16x3: null operand");
+  SK_REQUIRE(gemm_f16x3_shape_ok(M, N, K), "sk_gemm_f16x3: needs M >= 256, N >= 128, K >= 64 (got %lld x %lld x %lld)",
+             (long long)M, (long long)N, (long long)K);
+  SK_REQUIRE(M <= INT32_MAX && N <= INT32_MAX && K <= INT32_MAX, "sk_gemm_f16x3: dimension too large");
+  SK_REQUIRE(a->ld % 8 == 0 && b->ld % 8 == 0, "sk_gemm_f16x3: operand pitches must be multiples of 8 elements");
+  SK_REQUIRE(a->ld >= (a->mn_major ? M : K) && b->ld >= (b->mn_major ? N : K), "sk_gemm_f16x3: pitch below row length");
+  const uintptr_t al = (uintptr_t)a->hi | (uintptr_t)a->lo | (uintptr_t)b->hi | (uintptr_t)b->lo;
+  SK_REQUIRE((al & 15) == 0, "sk_gemm_f16x3: operands must be 16-byte aligned");
+  SK_REQUIRE(ldc >= N, "sk_gemm_f16x3: ldc below N");
+  SK_REQUIRE(epilogue >= SK_EPI_NONE && epilogue <= SK_EPI_RELU, "sk_gemm_f16x3: bad epilogue %d", epilogue);
+  SK_REQUIRE(!(epilogue == SK_EPI_BIAS || epilogue == SK_EPI_BIAS_RELU) || bias, "sk_gemm_f16x3: epilogue needs a bias");
+  SK_REQUIRE(encode_fn() != nullptr, "sk_gemm_f16x3: cuTensorMapEncodeTiled is not available from the driver");
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.a = a->hi; g.b = b->hi; g.c = c; g.bias = bias;
+  g.a_dtype = g.b_dtype = SK_F32;
+  g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.batch = 1;
+  g.epilogue = epilogue;
+  g.a_inv1 = a->scale + 1; g.b_inv1 = b->scale + 1;
+  g.accumulate = accumulate ? 1 : 0;
+  Operand oa, ob;
+  oa.mn_major = a->mn_major != 0; oa.ld = a->ld;
+  ob.mn_major = b->mn_major != 0; ob.ld = b->ld;
+  ProfScope ps(SK_PROF_GEMM_TC, 2.0 * (double)M * (double)N * (double)K);
+  return launch_gemm_tc2(g, KIND_F16X3, oa, ob, a->lo, a->ld, b->lo, b->ld, nullptr, nullptr);
 }
 
 }  // namespace sk

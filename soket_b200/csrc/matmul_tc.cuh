@@ -118,6 +118,9 @@ struct TcParams {
   int group_m;            // M-tiles per rasterisation group (tile_coords)
   const float *row_inv;   // fp16x3: 2^-e per output row / column (operand scales to undo)
   const float *col_inv;
+  const float *a_inv1;    // fp16x3 on pre-split operands: one inverse scale for all of A / all of B
+  const float *b_inv1;
+  int accumulate;         // epilogue adds the result to what C holds (in-place gradient accumulation)
   int *sched;             // CTA-pair kernel: {next tile, finished pairs} for dynamic tile scheduling (NULL = static)
 };
 

@@ -344,7 +344,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int row = m0 + q * 32 + lane;
       if (row < p.M && n0 < p.N) {
         float *crow = p.c + (int64_t)row * p.ldc;
-        const float rinv = (KIND == KIND_F16X3) ? __ldg(p.row_inv + row) : 1.f;
+        const float rinv = (KIND != KIND_F16X3) ? 1.f
+                           : p.row_inv ? __ldg(p.row_inv + row) : (p.a_inv1 ? __ldg(p.a_inv1) : 1.f);
+        const float cinv1 = (KIND == KIND_F16X3 && p.b_inv1) ? __ldg(p.b_inv1) : 1.f;
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           const int col = n0 + c0;
@@ -356,7 +358,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               if (KIND == KIND_F16X3) {
                 // undo the operand scales: exact powers of two, smaller factor first so that the
                 // intermediate cannot overflow when the result itself is representable
-                const float cinv = (p.col_inv && (full || col + j < p.N)) ? __ldg(p.col_inv + col + j) : 1.f;
+                const float cinv = p.col_inv ? ((full || col + j < p.N) ? __ldg(p.col_inv + col + j) : 1.f) : cinv1;
                 v = (v * fminf(rinv, cinv)) * fmaxf(rinv, cinv);
               }
               if (p.epilogue == SK_EPI_BIAS || p.epilogue == SK_EPI_BIAS_RELU) {
@@ -364,6 +366,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               }
               if (p.epilogue == SK_EPI_BIAS_RELU || p.epilogue == SK_EPI_RELU) v = fmaxf(v, 0.f);
               accum[c0 + j] = v;
+            }
+            if (p.accumulate) {   // C + A @ B: the partial adjoint already in C (autodiff.pyx:30-41)
+              if (full && vec_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 o = *reinterpret_cast<const float4 *>(crow + col + j);
+                  accum[c0 + j] = __fadd_rn(o.x, accum[c0 + j]); accum[c0 + j + 1] = __fadd_rn(o.y, accum[c0 + j + 1]);
+                  accum[c0 + j + 2] = __fadd_rn(o.z, accum[c0 + j + 2]); accum[c0 + j + 3] = __fadd_rn(o.w, accum[c0 + j + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < p.N) accum[c0 + j] = __fadd_rn(crow[col + j], accum[c0 + j]);
+              }
             }
             if (full && vec_ok) {
 #pragma unroll
@@ -428,6 +444,7 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
   p.epilogue = g.epilogue;
   p.row_inv = row_inv; p.col_inv = col_inv;
+  p.a_inv1 = g.a_inv1; p.b_inv1 = g.b_inv1; p.accumulate = g.accumulate;
   p.tiles_m = (int)((g.M + BM2 - 1) / BM2);
   p.tiles_n = (int)((g.N + BN2 - 1) / BN2);
   static const int group_env = getenv("SOKET_B200_GEMM_GROUP_M") ? atoi(getenv("SOKET_B200_GEMM_GROUP_M")) : 8;

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "matmul_split.cuh"
 #include "reduce.cuh"
 
 namespace sk {
@@ -90,6 +91,57 @@ __device__ __forceinline__ float affine(float xs, float r, float g, float b) {
   return __fadd_rn(__fmul_rn(g, __fmul_rn(xs, r)), b);
 }
 
+// Optional by-products of the LayerNorm kernels for the fp16x3 GEMM that consumes their result
+// (sk_layernorm_*_ex).  Forward: the output also as fp16 hi / lo with ONE power-of-two scale, chosen
+// BEFORE any element is computed from a bound of the output:
+//     |gamma * norm + beta| <= max|gamma| * sqrt(C) + max|beta|       (|norm| < sqrt(C): one element can
+//     carry at most the whole variance), plus the residual's own bound, times 1/keep under dropout
+// -- no pass over the data, no second kernel.  Backward: the bit pattern of max |dx| into a device
+// word (atomicMax), from which the adjoint's split pass takes its scale without a pass of its own.
+struct LnExtras {
+  __half *hi, *lo;            // (R, C) fp16, or null
+  float *scale;               // out: {scale, 1/scale, bound, 0}
+  const float *res_scale;     // the residual's scale4 (its [2] = bound of |residual|)
+  unsigned int *dx_amax;      // backward only, or null
+};
+
+// max over the block of two values; every thread gets both.  scratch: 16 floats.
+__device__ __forceinline__ void block_max2(float &a, float &b, float *scratch) {
+  a = warp_max(a); b = warp_max(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { scratch[warp] = a; scratch[8 + warp] = b; }
+  __syncthreads();
+  a = scratch[0]; b = scratch[8];
+#pragma unroll
+  for (int i = 1; i < kNT / 32; ++i) { a = fmaxf(a, scratch[i]); b = fmaxf(b, scratch[8 + i]); }
+  __syncthreads();
+}
+
+// the scale of the output split (all blocks compute the same value; block 0 publishes it)
+__device__ __forceinline__ float ln_split_scale(const LnExtras &ex, const float *gamma, const float *beta, int C,
+                                                bool has_residual, float r_keep, float *scratch) {
+  float gm = gamma ? 0.f : 1.f, bm = 0.f;
+  for (int i = threadIdx.x; i < C; i += kNT) {
+    if (gamma) gm = fmaxf(gm, fabsf(__ldg(gamma + i)));
+    if (beta) bm = fmaxf(bm, fabsf(__ldg(beta + i)));
+  }
+  block_max2(gm, bm, scratch);
+  float bound = gm * sqrtf((float)C) + bm;
+  if (has_residual) bound += ex.res_scale[2];
+  bound *= 1.0001f * r_keep;          // fp32 rounding of the output; dropout scales kept values by 1/keep
+  float sc, inv;
+  pow2_scale(bound, sc, inv);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ex.scale[0] = sc; ex.scale[1] = inv; ex.scale[2] = bound; ex.scale[3] = 0.f; }
+  return sc;
+}
+
+__device__ __forceinline__ void ln_store_split(const LnExtras &ex, int64_t elem, const float4 &o, float sc) {
+  uint2 h, l;
+  split4(o, sc, h, l);
+  *reinterpret_cast<uint2 *>(ex.hi + elem) = h;     // read next by the GEMM's TMA loads: keep in L2
+  *reinterpret_cast<uint2 *>(ex.lo + elem) = l;
+}
+
 // ------------------------------------------------------------------- LayerNorm
 // TPR threads cooperate on one row; each holds VPT float4 (the row lives in
 // registers between the statistics and the normalisation: x is read once).
@@ -98,9 +150,10 @@ __global__ void __launch_bounds__(kNT)
 ln_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
               const float *__restrict__ beta, const float *__restrict__ residual,
               float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-              int64_t R, int C, float eps, int relu, const DropSpec drop) {
-  __shared__ float smem[kNT / 32];
+              int64_t R, int C, float eps, int relu, const DropSpec drop, const LnExtras ex) {
+  __shared__ float smem[16];
   const uint64_t dseed = drop_seed(drop);
+  const float sc = ex.hi ? ln_split_scale(ex, gamma, beta, C, residual != nullptr, drop.keep < 1.f ? drop.r_keep : 1.f, smem) : 1.f;
   constexpr int RPB = kNT / TPR;  // rows per block
   const int t = threadIdx.x % TPR;
   const int C4 = C >> 2;
@@ -156,6 +209,7 @@ ln_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (drop.keep < 1.f) drop_fwd4(o, drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         st_stream(yr + i, o);
+        if (ex.hi) ln_store_split(ex, row * C + 4 * (int64_t)i, o, sc);
       }
     }
   }
@@ -172,9 +226,10 @@ ln_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ x,
               const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
               const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
               float *__restrict__ dresidual, float *__restrict__ part_g,
-              float *__restrict__ part_b, int64_t R, int C, const DropSpec drop) {
+              float *__restrict__ part_b, int64_t R, int C, const DropSpec drop, unsigned int *__restrict__ dx_amax) {
   __shared__ float smem[kNT / 32];
   const uint64_t dseed = drop_seed(drop);
+  float amax = 0.f;
   constexpr int RPB = kNT / TPR;
   const int t = threadIdx.x % TPR;
   const int grp = threadIdx.x / TPR;
@@ -248,8 +303,13 @@ ln_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ x,
         o.x = c0 + (a[j].x * r + c2 * xs[j].x); o.y = c0 + (a[j].y * r + c2 * xs[j].y);
         o.z = c0 + (a[j].z * r + c2 * xs[j].z); o.w = c0 + (a[j].w * r + c2 * xs[j].w);
         st_stream(dr + i, o);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
       }
     }
+  }
+  if (dx_amax) {
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(dx_amax, __float_as_uint(amax));
   }
   if (part_g) {
     const int64_t prow = (int64_t)blockIdx.x * RPB + grp;
@@ -327,9 +387,10 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
                      const float *__restrict__ y_out, int mask_mode, float *__restrict__ dx,
                      float *__restrict__ dresidual, float *__restrict__ part_g,
                      float *__restrict__ part_b, int64_t R, int C, int stages, int *__restrict__ sched,
-                     const DropSpec drop) {
+                     const DropSpec drop, unsigned int *__restrict__ dx_amax) {
   extern __shared__ __align__(128) uint8_t ln_sm[];
   const uint64_t dseed = drop_seed(drop);
+  float amax = 0.f;
   float *red = reinterpret_cast<float *>(ln_sm);
   uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
   volatile int *row_ring = reinterpret_cast<volatile int *>(ln_sm + 224);   // [kLnMaxStages] claimed rows
@@ -443,8 +504,13 @@ ln_bwd_staged_kernel(const float *__restrict__ adj, const float *__restrict__ x,
         o.x = c0 + (a[j].x * r + c2 * xs[j].x); o.y = c0 + (a[j].y * r + c2 * xs[j].y);
         o.z = c0 + (a[j].z * r + c2 * xs[j].z); o.w = c0 + (a[j].w * r + c2 * xs[j].w);
         st_stream(dr + i, o);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
       }
     }
+  }
+  if (dx_amax) {
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(dx_amax, __float_as_uint(amax));
   }
   if (part_g) {
     const int64_t prow = blockIdx.x;
@@ -472,10 +538,11 @@ __global__ void __launch_bounds__(kNT, 2)
 ln_fwd_staged_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
                      const float *__restrict__ beta, const float *__restrict__ residual,
                      float *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out,
-                     int64_t R, int C, float eps, int relu, int stages, const DropSpec drop) {
+                     int64_t R, int C, float eps, int relu, int stages, const DropSpec drop, const LnExtras ex) {
   extern __shared__ __align__(128) uint8_t ln_sm[];
   const uint64_t dseed = drop_seed(drop);
   float *red = reinterpret_cast<float *>(ln_sm);
+  const float sc = ex.hi ? ln_split_scale(ex, gamma, beta, C, residual != nullptr, drop.keep < 1.f ? drop.r_keep : 1.f, red) : 1.f;
   uint64_t *full = reinterpret_cast<uint64_t *>(ln_sm + 192);
   float *data = reinterpret_cast<float *>(ln_sm + kLnHeader);
   const int nbuf = residual ? 2 : 1;
@@ -557,6 +624,7 @@ ln_fwd_staged_kernel(const float *__restrict__ x, const float *__restrict__ gamm
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         if (drop.keep < 1.f) drop_fwd4(o, drop_mask4(row * C + 4 * (int64_t)i, dseed, drop.keep), drop.r_keep);
         st_stream(yr + i, o);
+        if (ex.hi) ln_store_split(ex, row * C + 4 * (int64_t)i, o, sc);
       }
     }
   }
@@ -620,7 +688,7 @@ ln_param_grads_kernel(const float *__restrict__ part_g, const float *__restrict_
 template <int TPR, int VPT>
 static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, const float *residual,
                          float *y, float *mean, float *rstd, int64_t R, int C, float eps, int relu,
-                         const DropSpec drop) {
+                         const DropSpec drop, const LnExtras ex) {
   constexpr int RPB = kNT / TPR;
   if (TPR == kNT) {
     int stages, bps = 1;
@@ -635,15 +703,15 @@ static int ln_fwd_launch(const float *x, const float *gamma, const float *beta, 
       }
       const int64_t cap = (int64_t)ctx().num_sms * bps;
       const int grid = (int)(R < cap ? R : cap);
-      ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
-      kern<<<grid, kNT, smem, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, stages, drop);
+      ProfScope ps(SK_PROF_LN_FWD, (double)R * C * ((residual ? 12.0 : 8.0) + (ex.hi ? 4.0 : 0.0)));
+      kern<<<grid, kNT, smem, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, stages, drop, ex);
       SK_LAUNCH_CHECK();
       return SK_OK;
     }
   }
   int grid = grid_for(R, RPB, 8);
-  ProfScope ps(SK_PROF_LN_FWD, (double)R * C * (residual ? 12.0 : 8.0));
-  ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, drop);
+  ProfScope ps(SK_PROF_LN_FWD, (double)R * C * ((residual ? 12.0 : 8.0) + (ex.hi ? 4.0 : 0.0)));
+  ln_fwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(x, gamma, beta, residual, y, mean, rstd, R, C, eps, relu, drop, ex);
   SK_LAUNCH_CHECK();
   return SK_OK;
 }
@@ -652,7 +720,7 @@ template <int TPR, int VPT>
 static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, const float *beta,
                          const float *mean, const float *rstd, const float *y_out, int mask_mode,
                          float *dx, float *dresidual, float *dgamma, float *dbeta, int64_t R, int C,
-                         const DropSpec drop) {
+                         const DropSpec drop, unsigned int *dx_amax) {
   constexpr int RPB = kNT / TPR;
   // persistent: each group walks many rows so the dgamma/dbeta partial matrix stays small
   int64_t need = (R + RPB - 1) / RPB;
@@ -684,10 +752,11 @@ static int ln_bwd_launch(const float *adj, const float *x, const float *gamma, c
         SK_CUDA(cudaMemsetAsync(sched_dev, 0, 2 * sizeof(int), stream()));
       }
       kern<<<grid, kNT, smem, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, part,
-                                          part ? part + P * C : nullptr, R, C, stages, sched_dev, drop);
+                                          part ? part + P * C : nullptr, R, C, stages, sched_dev, drop, dx_amax);
     } else {
       ln_bwd_kernel<TPR, VPT><<<grid, kNT, 0, stream()>>>(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx,
-                                                         dresidual, part, part ? part + P * C : nullptr, R, C, drop);
+                                                         dresidual, part, part ? part + P * C : nullptr, R, C, drop,
+                                                         dx_amax);
     }
   }
   SK_LAUNCH_CHECK();
@@ -1117,9 +1186,22 @@ using namespace sk;
 
 extern "C" {
 
-int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta, const float *residual,
-                     float *y, float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
-                     int relu) {
+static int ln_extras_fwd(const sk_ln_extras *in, const float *residual, int64_t cols, LnExtras &ex, const char *who) {
+  ex.hi = nullptr; ex.lo = nullptr; ex.scale = nullptr; ex.res_scale = nullptr; ex.dx_amax = nullptr;
+  if (!in || !in->split_hi) return SK_OK;
+  SK_REQUIRE(in->split_lo && in->split_scale, "%s: split_hi needs split_lo and split_scale", who);
+  SK_REQUIRE(!residual || in->residual_scale, "%s: the output split of a residual LayerNorm needs residual_scale "
+             "(the bound of |residual|)", who);
+  SK_REQUIRE(cols % 8 == 0, "%s: the output split needs cols %% 8 == 0 (got %lld)", who, (long long)cols);
+  SK_REQUIRE(al16(in->split_hi) && al16(in->split_lo), "%s: split buffers must be 16-byte aligned", who);
+  ex.hi = (__half *)in->split_hi; ex.lo = (__half *)in->split_lo;
+  ex.scale = in->split_scale; ex.res_scale = residual ? in->residual_scale : nullptr;
+  return SK_OK;
+}
+
+int sk_layernorm_fwd_ex(const float *x, const float *gamma, const float *beta, const float *residual,
+                        float *y, float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                        int relu, const sk_ln_extras *extras) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(x && y && mean && rstd, "sk_layernorm_fwd: null pointer");
@@ -1128,15 +1210,23 @@ int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta, cons
   SK_REQUIRE(al16(x) && al16(y) && (!gamma || al16(gamma)) && (!beta || al16(beta)) &&
                  (!residual || al16(residual)),
              "sk_layernorm_fwd: pointers must be 16-byte aligned");
+  LnExtras ex;
+  if ((rc = ln_extras_fwd(extras, residual, cols, ex, "sk_layernorm_fwd_ex"))) return rc;
   if (rows == 0) return SK_OK;
   const DropSpec off = {1.f, 1.f, 0ull, nullptr};
-  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, residual, y, mean, rstd, rows, (int)cols, eps, relu, off);
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, residual, y, mean, rstd, rows, (int)cols, eps, relu, off, ex);
   return SK_ERR_UNSUPPORTED;
 }
 
-int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y, float *mean,
-                             float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
-                             uint64_t *seed_out) {
+int sk_layernorm_fwd(const float *x, const float *gamma, const float *beta, const float *residual,
+                     float *y, float *mean, float *rstd, int64_t rows, int64_t cols, float eps,
+                     int relu) {
+  return sk_layernorm_fwd_ex(x, gamma, beta, residual, y, mean, rstd, rows, cols, eps, relu, nullptr);
+}
+
+int sk_layernorm_dropout_fwd_ex(const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                                float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
+                                uint64_t *seed_out, const sk_ln_extras *extras) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(x && y && mean && rstd && seed_out, "sk_layernorm_dropout_fwd: null pointer");
@@ -1145,19 +1235,27 @@ int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *be
   SK_REQUIRE(keep > 0.f && keep < 1.f, "sk_layernorm_dropout_fwd: keep rate must be in (0, 1)");
   SK_REQUIRE(al16(x) && al16(y) && (!gamma || al16(gamma)) && (!beta || al16(beta)),
              "sk_layernorm_dropout_fwd: pointers must be 16-byte aligned");
+  LnExtras ex;
+  if ((rc = ln_extras_fwd(extras, nullptr, cols, ex, "sk_layernorm_dropout_fwd_ex"))) return rc;
   // one draw per call from the same sequence as sk_dropout_fwd_seeded
   const uint64_t seed = g_dropout_seed + 0x632BE59BD9B4E019ull * (++g_dropout_calls);
   *seed_out = seed;
   if (rows == 0) return SK_OK;
   const DropSpec drop = {keep, (float)(1.0 / (double)keep), seed, rng_epoch_ptr()};
-  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, nullptr, y, mean, rstd, rows, (int)cols, eps, relu, drop);
+  LN_DISPATCH(ln_fwd_launch, x, gamma, beta, nullptr, y, mean, rstd, rows, (int)cols, eps, relu, drop, ex);
   return SK_ERR_UNSUPPORTED;
 }
 
-int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
-                     const float *mean, const float *rstd, const float *y_out, int mask_mode,
-                     float *dx, float *dgamma, float *dbeta, float *dresidual, int64_t rows,
-                     int64_t cols) {
+int sk_layernorm_dropout_fwd(const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                             float *rstd, int64_t rows, int64_t cols, float eps, int relu, float keep,
+                             uint64_t *seed_out) {
+  return sk_layernorm_dropout_fwd_ex(x, gamma, beta, y, mean, rstd, rows, cols, eps, relu, keep, seed_out, nullptr);
+}
+
+int sk_layernorm_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                        const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                        float *dx, float *dgamma, float *dbeta, float *dresidual, int64_t rows,
+                        int64_t cols, const sk_ln_extras *extras) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(adj && x && mean && rstd && dx, "sk_layernorm_bwd: null pointer");
@@ -1168,15 +1266,32 @@ int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const
   SK_REQUIRE(al16(adj) && al16(x) && al16(dx), "sk_layernorm_bwd: pointers must be 16-byte aligned");
   if (rows == 0) return SK_OK;
   const DropSpec off = {1.f, 1.f, 0ull, nullptr};
+  unsigned int *dx_amax = extras ? extras->dx_absmax : nullptr;
   LN_DISPATCH(ln_bwd_launch, adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dresidual, dgamma,
-              dbeta, rows, (int)cols, off);
+              dbeta, rows, (int)cols, off, dx_amax);
   return SK_ERR_UNSUPPORTED;
+}
+
+int sk_layernorm_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
+                     const float *mean, const float *rstd, const float *y_out, int mask_mode,
+                     float *dx, float *dgamma, float *dbeta, float *dresidual, int64_t rows,
+                     int64_t cols) {
+  return sk_layernorm_bwd_ex(adj, x, gamma, beta, mean, rstd, y_out, mask_mode, dx, dgamma, dbeta, dresidual, rows,
+                             cols, nullptr);
 }
 
 int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamma, const float *beta,
                              const float *mean, const float *rstd, int relu, float keep, float r_keep,
                              uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
                              int64_t cols) {
+  return sk_layernorm_dropout_bwd_ex(adj, x, gamma, beta, mean, rstd, relu, keep, r_keep, seed, dx, dgamma, dbeta,
+                                     rows, cols, nullptr);
+}
+
+int sk_layernorm_dropout_bwd_ex(const float *adj, const float *x, const float *gamma, const float *beta,
+                                const float *mean, const float *rstd, int relu, float keep, float r_keep,
+                                uint64_t seed, float *dx, float *dgamma, float *dbeta, int64_t rows,
+                                int64_t cols, const sk_ln_extras *extras) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(adj && x && mean && rstd && dx, "sk_layernorm_dropout_bwd: null pointer");
@@ -1187,7 +1302,7 @@ int sk_layernorm_dropout_bwd(const float *adj, const float *x, const float *gamm
   if (rows == 0) return SK_OK;
   const DropSpec drop = {keep, r_keep, seed, rng_epoch_ptr()};
   LN_DISPATCH(ln_bwd_launch, adj, x, gamma, beta, mean, rstd, nullptr, relu ? 1 : 0, dx, nullptr, dgamma,
-              dbeta, rows, (int)cols, drop);
+              dbeta, rows, (int)cols, drop, extras ? extras->dx_absmax : nullptr);
   return SK_ERR_UNSUPPORTED;
 }
 

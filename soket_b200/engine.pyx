@@ -27,9 +27,10 @@ from cpython.ref cimport PyObject
 import numpy as np
 
 from soket_b200._abi cimport *
-from soket_b200._core cimport ndarray, Buffer, _new_array, _check, _fptr, _as_device
+from soket_b200._core cimport ndarray, Buffer, SplitMat, _new_array, _check, _fptr, _as_device
 from soket_b200 import _core as B
 from soket_b200 import _fused as F
+import os as _os_env
 
 
 # ============================================================================ dtypes
@@ -1115,6 +1116,46 @@ def logsumexp(Tensor x, *axes, keepdims=False):
 
 
 # ============================================================================ fused ops
+_PRESPLIT = _os_env.environ.get('SOKET_B200_PRESPLIT', '1') != '0'
+
+
+def set_presplit(on):
+    """Linear layers on PRE-SPLIT GEMM operands (default on; SOKET_B200_PRESPLIT=0): each matrix of a
+    step is rewritten as fp16 hi / lo once -- the activations by the LayerNorm kernel that produces
+    them, a weight once per optimizer step, an adjoint once for dX and dW -- instead of inside every
+    GEMM call.  Off = every sk_linear_* call splits its own operands (round-1 behaviour)."""
+    global _PRESPLIT
+    _PRESPLIT = bool(on)
+
+
+def presplit_enabled():
+    return _PRESPLIT
+
+
+cdef inline bint _presplit_shapes(ndarray xd, ndarray wd):
+    """All three GEMMs of the layer (forward, dX, dW) fit the CTA-pair tcgen05 kernel."""
+    if xd._ndim != 2 or wd._ndim != 2 or xd._code != SK_F32 or wd._code != SK_F32:
+        return False
+    cdef int64_t Bn = xd._shape[0], I = xd._shape[1], O = wd._shape[1]
+    return Bn >= 256 and I >= 256 and O >= 128 and I % 8 == 0 and O % 8 == 0 and wd._is_contiguous()
+
+
+cdef object _take_sole_partial(Tensor x):
+    """The one partial adjoint x has received so far, if the caller delivers the LAST one and may add
+    into it (the block input of model.py:17-37: the residual branch's adjoint arrives first, then
+    Linear1's dX) -- the dX GEMM then accumulates in its epilogue instead of a separate pass."""
+    if x._partials is None or len(x._partials) != 1 or x._pending != 1:
+        return None
+    p, o = x._partials[0]
+    if not o or not _sole_view(p):
+        return None
+    cdef ndarray a = <ndarray> p
+    if a._code != SK_F32 or a._ndim != 2 or not a._is_contiguous() or a.shape != x.shape:
+        return None
+    x._partials.pop()
+    return p
+
+
 cdef inline object _slot(object t):
     """The gradient-arena slot of a LEAF parameter (or None).  Only leaves: a non-leaf's adjoint may
     be consumed by reference, and a slot is rewritten on the next backward."""
@@ -1128,10 +1169,13 @@ class _LinearOp(Op):
     dZ = relu mask * adj (one pass), dX = dZ @ W.T, dW = X.T @ dZ (both on .T views,
     backward.pyx:720-736), db = column sum (autodiff.pyx:43-101 done eagerly)."""
     name = 'linear'
-    def __init__(self, relu):
+    def __init__(self, relu, xs=None):
         self.relu = relu
+        self.xs = xs          # the input's SplitMat (pre-split path): reused by dW = X.T @ adj
     def bwd(self, node, adj):
         x, w, b = node._inputs
+        if self.xs is not None:
+            return self._bwd_presplit(node, adj)
         if self.relu:
             adj = B.relu_backward(node._data, adj)   # y > 0  <=>  pre-activation > 0
         elif not adj.is_contiguous:
@@ -1160,11 +1204,41 @@ class _LinearOp(Op):
         return (gx, gw, gb)
 
 
+    def _bwd_presplit(self, node, adj):
+        """backward.pyx:704-742 on shared splits: adj is split ONCE (its column sums = the bias
+        gradient, autodiff.pyx:84), dX = adj @ W.T reuses the forward's weight split, dW = X.T @ adj
+        the forward's input split."""
+        x, w, b = node._inputs
+        if self.relu:
+            adj = B.relu_backward(node._data, adj)
+        elif not adj.is_contiguous:
+            adj = B.ascontiguousarray(adj)
+        gb = None
+        if b is not None and b.requires_grad:
+            asp, gb = B.split_f16(adj, True, _slot(b))
+        else:
+            asp = B.get_split(adj)
+        gx = gw = None
+        if x.requires_grad:
+            acc = _take_sole_partial(<Tensor> x)
+            gx = B.gemm_split(asp, False, B.get_split(w._data), True, None, False, acc, acc is not None)
+        if w.requires_grad:
+            gw = B.gemm_split(self.xs, True, asp, False, None, False, _slot(w), False)
+        return (gx, gw, gb)
+
+
 def linear(Tensor x, Tensor w, b=None, bint relu=False):
     if x._data.ndim < 2 or w._data.ndim != 2:
         raise RuntimeError('Both tensors must be atleast 2D for matmul!')
     if x.shape[-1] != w.shape[0]:
         raise RuntimeError('Incompatible shapes for matmul!')
+    cdef ndarray xc
+    if _PRESPLIT and _presplit_shapes(x._data, w._data) and (b is None or (<Tensor> b)._dtype.name == 'float32'):
+        xc = x._data if x._data.is_contiguous else B.ascontiguousarray(x._data)
+        xs = B.get_split(xc)
+        y = B.gemm_split(xs, False, B.get_split(w._data), False,
+                         None if b is None else (<Tensor> b)._data, relu)
+        return Tensor._from_op(_LinearOp(relu, xs), (x, w, b), y, x._dtype)
     xd = x._data if x._data.ndim == 2 else B.reshape(x._data, (-1, x.shape[-1]))
     y = B.linear(xd, w._data, None if b is None else (<Tensor> b)._data, relu)
     if x._data.ndim != 2:
@@ -1172,8 +1246,7 @@ def linear(Tensor x, Tensor w, b=None, bint relu=False):
     return Tensor._from_op(_LinearOp(relu), (x, w, b), y, x._dtype)
 
 
-import os as _os
-_FUSE_DROPOUT = _os.environ.get('SOKET_B200_FUSE_DROPOUT', '1') != '0'
+_FUSE_DROPOUT = _os_env.environ.get('SOKET_B200_FUSE_DROPOUT', '1') != '0'
 
 
 def set_dropout_fusion(on):
@@ -1197,7 +1270,7 @@ class _LayerNormOp(Op):
             want_p = (g is not None and g.requires_grad) or (b is not None and b.requires_grad)
             dx, dg, db = F.layernorm_dropout_bwd(
                 adj, x._data, None if g is None else g._data, None if b is None else b._data,
-                self.mean, self.rstd, self.relu, keep, 1.0 / keep, seed, want_p, _slot(g), _slot(b))
+                self.mean, self.rstd, self.relu, keep, 1.0 / keep, seed, want_p, _slot(g), _slot(b), _PRESPLIT)
             return (dg, db, dx if x.requires_grad else None, None)
         mode = 0
         if self.relu:
@@ -1207,7 +1280,7 @@ class _LayerNormOp(Op):
         dx, dg, db, dres = F.layernorm_bwd(
             adj, x._data, None if g is None else g._data, None if b is None else b._data,
             self.mean, self.rstd, node._data if mode == 2 else None, mode,
-            want_res and mode == 2, want_p, _slot(g), _slot(b))
+            want_res and mode == 2, want_p, _slot(g), _slot(b), _PRESPLIT)
         if want_res and mode != 2:
             dres = adj    # plain residual add: the adjoint passes through (aliased)
         return (dg, db, dx if x.requires_grad else None, dres if want_res else None)
@@ -1229,7 +1302,7 @@ def layer_norm_dropout(Tensor X, weight, bias, eps, bint relu, keep_rate):
         xd = B.ascontiguousarray(xd)
     y, mean, rstd, seed = F.layernorm_dropout_fwd(
         xd, None if weight is None else (<Tensor> weight)._data.reshape(-1),
-        None if bias is None else (<Tensor> bias)._data.reshape(-1), eps, relu, keep_rate)
+        None if bias is None else (<Tensor> bias)._data.reshape(-1), eps, relu, keep_rate, _PRESPLIT)
     op = _LayerNormOp(mean, rstd, relu, False, (keep_rate, seed))
     return Tensor._from_op(op, (weight, bias, X, None), y, X._dtype)
 
@@ -1255,11 +1328,16 @@ def layer_norm(Tensor X, weight=None, bias=None, eps=1e-5, bint relu=False, resi
     if X._dtype.name != 'float32' or cols % 4 != 0 or cols > 8192:
         return _layer_norm_unfused(X, weight, bias, eps, relu, residual)
     rd = None
+    rsplit = None
     if residual is not None:
-        rd = B.ascontiguousarray(B.reshape((<Tensor> residual)._data, xd.shape))
+        rd = (<Tensor> residual)._data
+        if rd.shape != xd.shape or not rd.is_contiguous:
+            rd = B.ascontiguousarray(B.reshape(rd, xd.shape))
+        elif _PRESPLIT and isinstance((<ndarray> rd)._meta, SplitMat) and (<SplitMat> (<ndarray> rd)._meta).valid_for(<ndarray> rd):
+            rsplit = (<ndarray> rd)._meta     # carries the bound of |residual| the output's scale needs
     y, mean, rstd = F.layernorm_fwd(xd, None if weight is None else (<Tensor> weight)._data.reshape(-1),
                                     None if bias is None else (<Tensor> bias)._data.reshape(-1),
-                                    rd, eps, relu)
+                                    rd, eps, relu, _PRESPLIT and (residual is None or rsplit is not None), rsplit)
     if X._data.ndim != 2:
         y = B.reshape(y, X.shape)
     op = _LayerNormOp(mean, rstd, relu, residual is not None)
