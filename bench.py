@@ -511,6 +511,34 @@ def run_ours(args, env):
     ms_e2e = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3)   # device events vs host wall clock
     clock_info = clocks.stop() if env.rank == 0 else None
 
+    # ---- data parallel: where the step's time goes (phase events; nsys is not in the image) ----
+    dp_timeline = None
+    if rdv is not None:
+        acc = {"forward": 0.0, "backward": 0.0, "comm_after_backward": 0.0, "optimizer_after_comm": 0.0, "step": 0.0}
+        evs = [sk.Event() for _ in range(3)]
+        barrier()
+        for _ in range(args.steps):
+            evs[0].record()
+            loss = crit(model(Xd), yd)
+            evs[1].record()
+            loss.backward()
+            evs[2].record()
+            ddp.step()
+            ev_red, ev_done = ddp.timeline_events()
+            ev_done.synchronize()
+            acc["forward"] += evs[0].elapsed_ms(evs[1])
+            acc["backward"] += evs[1].elapsed_ms(evs[2])
+            tail = max(evs[2].elapsed_ms(ev_red), 0.0)         # all-reduce still running after backward ended
+            acc["comm_after_backward"] += tail
+            acc["optimizer_after_comm"] += max(evs[2].elapsed_ms(ev_done) - tail, 0.0)
+            acc["step"] += evs[0].elapsed_ms(ev_done)
+        dp_timeline = {k: v / args.steps for k, v in acc.items()}
+        dp_timeline["note"] = ("ms per step on this rank, CUDA events: forward / backward on the compute stream; "
+                               "comm_after_backward = the last bucket's all-reduce finishing after backward's last "
+                               "kernel (exposed communication); optimizer_after_comm = the last buckets' Adam + weight "
+                               "re-split after that (exposed update); each step drained before the next starts")
+        barrier()
+
     dp_check = None
     if rdv is not None:
         ms = max(rdv.all_gather_float(ms))
@@ -576,6 +604,7 @@ def run_ours(args, env):
         }
         if dp_check is not None:
             line["dp_check"] = dp_check
+            line["dp_timeline"] = dp_timeline
         if env.world == 1 and not args.no_cpu_baseline:
             # free the benchmark's device state first: the parity model is a second 272 M-parameter net
             ref = CpuReference(args, install_compat=True)

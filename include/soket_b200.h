@@ -192,6 +192,31 @@ int sk_ewise_unary(int op, const sk_array *a, sk_array *out);
  * astype, broadcast materialisation, slice __setitem__ (tensor.pyx:948). */
 int sk_copy(const sk_array *src, sk_array *dst);
 int sk_fill(sk_array *dst, double fvalue, int64_t ivalue, int value_is_int);
+/* A CHAIN of float32 elementwise / scalar / unary ops as ONE launch (lazy mode, tensor.pyx:24-51,
+ * 790-810: with soket.lazy() the graph is known before anything runs, so a run of elementwise nodes
+ * is evaluated in registers instead of one HBM pass per node).  The chain is a small accumulator
+ * program interpreted per element -- every step is the same single fp32 operation the unfused kernel
+ * would have performed, in the same order, so the result is bit-identical to the op-by-op evaluation:
+ *   SK_F_LOAD   acc = operand               SK_F_STORE  temp[idx] = acc
+ *   SK_F_BIN    acc = acc (sub) operand     (rev: operand (sub) acc), sub = sk_binary_op ADD..MINIMUM
+ *   SK_F_UN     acc = (sub) acc             sub = sk_unary_op
+ * operand = an input array (src SK_F_IN: full-size, a last-axis vector of `cols` elements, or a single
+ * element), a constant (SK_F_CONST) or a temporary (SK_F_TEMP, 3 of them). */
+#define SK_FUSED_MAX_OPS 48
+#define SK_FUSED_MAX_INPUTS 8
+typedef enum { SK_F_LOAD = 0, SK_F_STORE = 1, SK_F_BIN = 2, SK_F_UN = 3 } sk_fused_code;
+typedef enum { SK_F_IN = 1, SK_F_CONST = 2, SK_F_TEMP = 3 } sk_fused_src;
+typedef enum { SK_F_FULL = 0, SK_F_VECTOR = 1, SK_F_SINGLE = 2 } sk_fused_input_kind;
+typedef struct {
+  int n_ops, n_in;
+  unsigned char code[SK_FUSED_MAX_OPS], sub[SK_FUSED_MAX_OPS], src[SK_FUSED_MAX_OPS], idx[SK_FUSED_MAX_OPS],
+      rev[SK_FUSED_MAX_OPS];
+  float cst[SK_FUSED_MAX_OPS];          /* the constant of a SK_F_CONST operand */
+  const float *in[SK_FUSED_MAX_INPUTS];
+  int in_kind[SK_FUSED_MAX_INPUTS];
+  int64_t n, cols;                      /* elements of the result; length of the last axis */
+} sk_fused_program;
+int sk_ewise_fused(const sk_fused_program *prog, float *out);
 /* relu backward: out = (x > 0) * adj  (backward.pyx:849-874) in one pass */
 int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out);
 
@@ -393,6 +418,13 @@ int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *gr
                      float *const *m, float *const *v, const int64_t *sizes, double lr,
                      double beta1, double beta2, double eps, double weight_decay,
                      const double *bias_state, int first_step, double grad_scale);
+/* sk_adam_step / sk_adam_step_dev (bias_state != NULL) that also leaves the bit pattern of max |p_new| of
+ * tensor i in the device word amax[i] (NULL entries: skipped; the caller zeroes the words): the scale
+ * of the weight's fp16x3 operand split (sk_split_f16 amax_bits) without a pass over the weight. */
+int sk_adam_step_amax(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                      float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                      const double *bias_state, int first_step, double grad_scale, unsigned int *const *amax);
 int sk_adam_bias_advance(double *bias_state, double beta1, double beta2);
 
 /* ------------------------------------------------------------- data parallel

@@ -118,6 +118,32 @@ cdef extern from "soket_b200.h" nogil:
     int sk_ewise_scalar(int op, const sk_array *a, double fscalar, int64_t iscalar,
                         int scalar_is_int, int reverse, sk_array *out)
     int sk_ewise_unary(int op, const sk_array *a, sk_array *out)
+    enum: SK_FUSED_MAX_OPS
+    enum: SK_FUSED_MAX_INPUTS
+    enum: SK_F_LOAD
+    enum: SK_F_STORE
+    enum: SK_F_BIN
+    enum: SK_F_UN
+    enum: SK_F_IN
+    enum: SK_F_CONST
+    enum: SK_F_TEMP
+    enum: SK_F_FULL
+    enum: SK_F_VECTOR
+    enum: SK_F_SINGLE
+    ctypedef struct sk_fused_program:
+        int n_ops
+        int n_in
+        unsigned char code[48]
+        unsigned char sub[48]
+        unsigned char src[48]
+        unsigned char idx[48]
+        unsigned char rev[48]
+        float cst[48]
+        const float *inp "in" [8]
+        int in_kind[8]
+        int64_t n
+        int64_t cols
+    int sk_ewise_fused(const sk_fused_program *prog, float *out)
     int sk_copy(const sk_array *src, sk_array *dst)
     int sk_fill(sk_array *dst, double fvalue, int64_t ivalue, int value_is_int)
     int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out)
@@ -214,6 +240,10 @@ cdef extern from "soket_b200.h" nogil:
                          float *const *m, float *const *v, const int64_t *sizes, double lr,
                          double beta1, double beta2, double eps, double weight_decay,
                          const double *bias_state, int first_step, double grad_scale)
+    int sk_adam_step_amax(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                          float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                          const double *bias_state, int first_step, double grad_scale, unsigned int *const *amax)
     int sk_adam_bias_advance(double *bias_state, double beta1, double beta2)
 
     int sk_nccl_available()

@@ -1428,6 +1428,13 @@ def new_absmax_word(ndarray owner=None):
     return a
 
 
+def bind_absmax_word(ndarray word, ndarray x):
+    """Attach a device word a kernel has filled with the bit pattern of max |x| to x."""
+    cdef AbsMax a = AbsMax.__new__(AbsMax)
+    a.word = word
+    bind_absmax(a, x)
+
+
 def bind_absmax(AbsMax a, ndarray x):
     a.version = x._buf.version
     a.epoch = _GRAPH_EPOCH
@@ -1443,6 +1450,8 @@ def split_f16(x, want_colsum=False, out_colsum=None):
     if a._ndim != 2 or a._code != SK_F32:
         raise TypeError('split_f16: expected a 2-D float32 array')
     a = a._compact()
+    if a._shape[1] % 4 != 0 and a._shape[0] > 1:
+        raise ValueError('split_f16: the row length must be a multiple of 4 elements (16-byte aligned rows)')
     cdef SplitMat m = _new_split(a._shape[0], a._shape[1])
     cdef const unsigned int *amax = NULL
     cdef AbsMax am

@@ -264,6 +264,10 @@ def accumulate_(ndarray acc, ndarray part):
     return acc
 
 
+cdef inline bint _wants_amax(ndarray p):
+    return p._ndim == 2 and p._shape[0] >= 256 and p._shape[1] >= 128 and p._code == SK_F32
+
+
 cdef class _PtrLists:
     """Host-side pointer lists for the multi-tensor optimiser kernels."""
     cdef float **p
@@ -314,7 +318,7 @@ def adam_bias_advance(ndarray state, double beta1, double beta2):
 
 def adam_step(list params, list grads, list m, list v, double lr, double beta1, double beta2,
               double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
-              bint first_step, double grad_scale=1.0, bias_state=None):
+              bint first_step, double grad_scale=1.0, bias_state=None, bint emit_absmax=True):
     """In-place Adam over all tensors in ONE launch (optim.pyx:201-269).  With `bias_state`
     (device float64 {beta1^t, beta2^t}) the kernel forms the bias corrections itself and the
     two host scalars are ignored (graph-capturable form)."""
@@ -329,6 +333,34 @@ def adam_step(list params, list grads, list m, list v, double lr, double beta1, 
         L.p[i] = _fptr(p); L.g[i] = _fptr(g)
         L.m[i] = _fptr(<ndarray> m[i]); L.v[i] = _fptr(<ndarray> v[i])
         L.sizes[i] = p._numel()
+    # weight matrices a Linear layer will re-split for its GEMMs get the |max| of their NEW values as a
+    # by-product (one zeroed word each; see sk_adam_step_amax)
+    cdef list wanted = [i for i in range(n) if _wants_amax(<ndarray> params[i])]
+    cdef unsigned int **aw = NULL
+    cdef ndarray words = None
+    cdef int64_t nw
+    cdef int k
+    if wanted and emit_absmax:
+        nw = len(wanted)
+        words = _new_array(1, &nw, SK_U32)
+        _check(sk_memset(<void *> words._ptr, 0, <size_t> nw * 4))
+        aw = <unsigned int **> malloc(n * sizeof(unsigned int *))
+        if aw == NULL:
+            raise MemoryError()
+        for i in range(n):
+            aw[i] = NULL
+        for k, i in enumerate(wanted):
+            aw[i] = (<unsigned int *> words._ptr) + k
+        try:
+            _check(sk_adam_step_amax(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
+                                     one_minus_beta1_t, one_minus_beta2_t,
+                                     _bias_ptr(<ndarray> bias_state) if bias_state is not None else NULL,
+                                     first_step, grad_scale, aw))
+        finally:
+            free(aw)
+        for k, i in enumerate(wanted):
+            _B.bind_absmax_word(words[k:k + 1], <ndarray> params[i])
+        return
     if bias_state is not None:
         _check(sk_adam_step_dev(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
                                 _bias_ptr(<ndarray> bias_state), first_step, grad_scale))

@@ -8,7 +8,7 @@ mirrors ``import soket`` / ``soket.nn`` / ``soket.optim`` of the reference
 (soket/__init__.py:1-7) for code that runs entirely on the GPU device.
 """
 from soket_b200.engine import (  # noqa: F401
-    Tensor, DType, Device, DeviceType, gpu, cpu, promote_types, lazy, LazyState,
+    Tensor, DType, Device, DeviceType, gpu, cpu, promote_types, lazy, LazyState, lazy_stats,
     float16, float32, float64, int8, uint8, int16, uint16, int32, uint32, int64, uint64, bool_,
     rand, randn, randb, zeros, ones, empty, full, one_hot,
     zeros_like, ones_like, one_like, empty_like, rand_like, randn_like,

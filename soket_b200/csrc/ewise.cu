@@ -62,6 +62,14 @@ __device__ __forceinline__ float pow_special(float a, float e, int kind) {
     default: return powf(a, e);
   }
 }
+__device__ __forceinline__ int pow_kind_dev(float e) {
+  if (e == 2.0f) return POW_SQUARE;
+  if (e == 0.5f) return POW_SQRT;
+  if (e == -0.5f) return POW_RSQRT;
+  if (e == -1.0f) return POW_RECIP;
+  if (e == 1.0f) return POW_ID;
+  return POW_GENERIC;
+}
 static int pow_kind(double e) {
   if (e == 2.0) return POW_SQUARE;
   if (e == 0.5) return POW_SQRT;
@@ -659,6 +667,135 @@ static void fill_desc(GenDesc &d, const Collapsed<N> &c, int ia, int ib, int io)
 template <template <int> class K>
 struct DispatchBinary;
 
+
+// ------------------------------------------------------------------ fused elementwise chains (lazy mode)
+// One thread walks the accumulator program for U groups of W elements.  The program is uniform across
+// the grid, so the per-step switch costs no divergence; what is saved is one HBM round trip per fused
+// node (8-12 B/elem each).  Every arithmetic step calls the SAME functors as the unfused kernels.
+template <int W>
+struct FVec { float v[W]; };
+
+template <int W>
+__device__ __forceinline__ FVec<W> fused_operand(const sk_fused_program &p, int k, int64_t e, const FVec<W> (&tmp)[3]) {
+  FVec<W> o;
+  const int src = p.src[k], idx = p.idx[k];
+  if (src == SK_F_CONST) {
+#pragma unroll
+    for (int c = 0; c < W; ++c) o.v[c] = p.cst[k];
+  } else if (src == SK_F_TEMP) {
+    o = idx == 0 ? tmp[0] : (idx == 1 ? tmp[1] : tmp[2]);
+  } else {
+    const float *in = p.in[idx];
+    const int kind = p.in_kind[idx];
+    if (kind == SK_F_SINGLE) {
+      const float s = __ldg(in);
+#pragma unroll
+      for (int c = 0; c < W; ++c) o.v[c] = s;
+    } else {
+      const int64_t at = kind == SK_F_FULL ? e : e % p.cols;
+      if (W == 4) {
+        const float4 q = kind == SK_F_FULL ? ld_stream(reinterpret_cast<const float4 *>(in + at))
+                                           : __ldg(reinterpret_cast<const float4 *>(in + at));
+        o.v[0] = q.x; o.v[1 % W] = q.y; o.v[2 % W] = q.z; o.v[3 % W] = q.w;
+      } else {
+        o.v[0] = in[at];
+      }
+    }
+  }
+  return o;
+}
+
+template <int OP, int W>
+__device__ __forceinline__ void fused_bin(FVec<W> &acc, const FVec<W> &o, bool rev, float cst, bool scalar_pow) {
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    if (OP == SK_OP_POW && scalar_pow && !rev) acc.v[c] = pow_special(acc.v[c], cst, pow_kind_dev(cst));
+    else acc.v[c] = rev ? BinF32<OP>::apply(o.v[c], acc.v[c]) : BinF32<OP>::apply(acc.v[c], o.v[c]);
+  }
+}
+
+template <int W, int U>
+__global__ void __launch_bounds__(kThreads)
+fused_ewise_kernel(const __grid_constant__ sk_fused_program p, float *__restrict__ out) {
+  const int64_t groups = p.n / W;
+  const int64_t stride = (int64_t)gridDim.x * kThreads * U;
+  for (int64_t base = (int64_t)blockIdx.x * kThreads * U + threadIdx.x; base < groups; base += stride) {
+    FVec<W> acc[U], tmp[U][3];
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+#pragma unroll
+      for (int c = 0; c < W; ++c) { acc[j].v[c] = 0.f; tmp[j][0].v[c] = 0.f; tmp[j][1].v[c] = 0.f; tmp[j][2].v[c] = 0.f; }
+    for (int k = 0; k < p.n_ops; ++k) {
+      const int code = p.code[k], sub = p.sub[k];
+      if (code == SK_F_STORE) {
+        const int idx = p.idx[k];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          if (idx == 0) tmp[j][0] = acc[j];
+          else if (idx == 1) tmp[j][1] = acc[j];
+          else tmp[j][2] = acc[j];
+        }
+        continue;
+      }
+      if (code == SK_F_UN) {
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+#pragma unroll
+          for (int c = 0; c < W; ++c) {
+            float a = acc[j].v[c];
+            switch (sub) {
+              case SK_UOP_NEG: a = UnF32<SK_UOP_NEG>::apply(a); break;
+              case SK_UOP_EXP: a = UnF32<SK_UOP_EXP>::apply(a); break;
+              case SK_UOP_LOG: a = UnF32<SK_UOP_LOG>::apply(a); break;
+              case SK_UOP_SQRT: a = UnF32<SK_UOP_SQRT>::apply(a); break;
+              case SK_UOP_RELU: a = UnF32<SK_UOP_RELU>::apply(a); break;
+              default: a = UnF32<SK_UOP_ABS>::apply(a); break;
+            }
+            acc[j].v[c] = a;
+          }
+        continue;
+      }
+      FVec<W> o[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int64_t g = base + (int64_t)j * kThreads;
+        if (g < groups) o[j] = fused_operand<W>(p, k, g * W, tmp[j]);
+        else {
+#pragma unroll
+          for (int c = 0; c < W; ++c) o[j].v[c] = 1.f;
+        }
+      }
+      if (code == SK_F_LOAD) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) acc[j] = o[j];
+        continue;
+      }
+      const bool rev = p.rev[k] != 0, spow = p.src[k] == SK_F_CONST;
+      const float cst = p.cst[k];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        switch (sub) {
+          case SK_OP_ADD: fused_bin<SK_OP_ADD, W>(acc[j], o[j], rev, cst, spow); break;
+          case SK_OP_SUB: fused_bin<SK_OP_SUB, W>(acc[j], o[j], rev, cst, spow); break;
+          case SK_OP_MUL: fused_bin<SK_OP_MUL, W>(acc[j], o[j], rev, cst, spow); break;
+          case SK_OP_DIV: fused_bin<SK_OP_DIV, W>(acc[j], o[j], rev, cst, spow); break;
+          case SK_OP_POW: fused_bin<SK_OP_POW, W>(acc[j], o[j], rev, cst, spow); break;
+          case SK_OP_MAXIMUM: fused_bin<SK_OP_MAXIMUM, W>(acc[j], o[j], rev, cst, spow); break;
+          default: fused_bin<SK_OP_MINIMUM, W>(acc[j], o[j], rev, cst, spow); break;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t g = base + (int64_t)j * kThreads;
+      if (g < groups) {
+        if (W == 4) st_stream(reinterpret_cast<float4 *>(out) + g, make_float4(acc[j].v[0], acc[j].v[1 % W], acc[j].v[2 % W], acc[j].v[3 % W]));
+        else out[g] = acc[j].v[0];
+      }
+    }
+  }
+}
+
 #define SK_BIN_SWITCH(op, CALL)                  \
   switch (op) {                                  \
     case SK_OP_ADD: CALL(SK_OP_ADD); break;      \
@@ -968,6 +1105,45 @@ int sk_fill(sk_array *dst, double fvalue, int64_t ivalue, int value_is_int) {
   fill_desc<1>(d, c, -1, -1, 0);
   int cls = dtype_is_float(dst->dtype) ? 1 : 2;
   return launch_generic(d, cls);
+}
+
+int sk_ewise_fused(const sk_fused_program *prog, float *out) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(prog && out, "sk_ewise_fused: null pointer");
+  const sk_fused_program &p = *prog;
+  SK_REQUIRE(p.n_ops >= 1 && p.n_ops <= SK_FUSED_MAX_OPS && p.n_in >= 0 && p.n_in <= SK_FUSED_MAX_INPUTS,
+             "sk_ewise_fused: program of %d ops / %d inputs out of range", p.n_ops, p.n_in);
+  SK_REQUIRE(p.n >= 0 && p.cols >= 1, "sk_ewise_fused: bad sizes");
+  SK_REQUIRE(p.code[0] == SK_F_LOAD, "sk_ewise_fused: a program starts with a load");
+  bool vec = p.n % 4 == 0 && aligned16(out);
+  for (int k = 0; k < p.n_ops; ++k) {
+    SK_REQUIRE(p.code[k] <= SK_F_UN, "sk_ewise_fused: bad code at op %d", k);
+    if (p.code[k] == SK_F_STORE) { SK_REQUIRE(p.idx[k] < 3, "sk_ewise_fused: 3 temporaries"); continue; }
+    if (p.code[k] == SK_F_UN) { SK_REQUIRE(p.sub[k] <= SK_UOP_ABS, "sk_ewise_fused: bad unary op"); continue; }
+    if (p.code[k] == SK_F_BIN) SK_REQUIRE(p.sub[k] <= SK_OP_MINIMUM, "sk_ewise_fused: bad binary op");
+    SK_REQUIRE(p.src[k] >= SK_F_IN && p.src[k] <= SK_F_TEMP, "sk_ewise_fused: bad operand source at op %d", k);
+    if (p.src[k] == SK_F_TEMP) SK_REQUIRE(p.idx[k] < 3, "sk_ewise_fused: 3 temporaries");
+    if (p.src[k] == SK_F_IN) SK_REQUIRE(p.idx[k] < p.n_in, "sk_ewise_fused: input index out of range at op %d", k);
+  }
+  for (int i = 0; i < p.n_in; ++i) {
+    SK_REQUIRE(p.in[i] != nullptr && p.in_kind[i] >= SK_F_FULL && p.in_kind[i] <= SK_F_SINGLE, "sk_ewise_fused: bad input %d", i);
+    if (p.in_kind[i] != SK_F_SINGLE) vec = vec && aligned16(p.in[i]);
+    if (p.in_kind[i] == SK_F_VECTOR) vec = vec && p.cols % 4 == 0;
+  }
+  if (p.n == 0) return SK_OK;
+  double bytes = 4.0 * (double)p.n;
+  for (int i = 0; i < p.n_in; ++i) bytes += p.in_kind[i] == SK_F_FULL ? 4.0 * (double)p.n : 0.0;
+  ProfScope ps(SK_PROF_EWISE, bytes);
+  if (vec) {
+    int grid = grid_for(p.n / 4, kThreads * 2, 8);
+    fused_ewise_kernel<4, 2><<<grid, kThreads, 0, stream()>>>(p, out);
+  } else {
+    int grid = grid_for(p.n, kThreads * 2, 8);
+    fused_ewise_kernel<1, 2><<<grid, kThreads, 0, stream()>>>(p, out);
+  }
+  SK_LAUNCH_CHECK();
+  return SK_OK;
 }
 
 int sk_relu_bwd(const sk_array *x, const sk_array *adj, sk_array *out) {

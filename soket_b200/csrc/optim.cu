@@ -7,6 +7,8 @@
 // contracted into FMA) in the reference's order, so given identical gradients
 // the update is bit-identical to the NumPy path.  12 B/param (SGD), 28 B/param
 // (Adam) of HBM traffic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sk {
@@ -38,6 +40,10 @@ struct AdamArgs {
   // capturable variant: {beta1^t, beta2^t} as doubles in DEVICE memory (advanced by
   // adam_bias_advance_kernel), so that a CUDA-graph replay sees the current bias corrections
   const double *bias_state;
+  // optional by-product: the bit pattern of max |p_new| per tensor (atomicMax into a zeroed word), from which
+  // the weight's fp16x3 operand split takes its scale without a pass of its own (sk_split_f16 amax_bits)
+  unsigned int *amax[kMaxTensors];
+  int total_blocks;   // chunks over all tensors; the grid may be smaller (capped) and strides over them
 };
 
 template <typename A>
@@ -104,8 +110,10 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
 }
 
 __global__ void __launch_bounds__(kOT) adam_kernel(const __grid_constant__ AdamArgs a) {
-  const int t = find_tensor(a, blockIdx.x);
-  const int64_t base = (int64_t)(blockIdx.x - a.block_start[t]) * kChunk;
+ for (int blk = blockIdx.x; blk < a.total_blocks; blk += gridDim.x) {
+  const int t = find_tensor(a, blk);
+  const int64_t base = (int64_t)(blk - a.block_start[t]) * kChunk;
+  float amax = 0.f;
   float *p = a.p[t];
   const float *g = a.g[t];
   float *m = a.m[t];
@@ -127,16 +135,22 @@ __global__ void __launch_bounds__(kOT) adam_kernel(const __grid_constant__ AdamA
         float4 vv = a.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4 *>(v + i);
         adam_one(pv.x, gv.x, mv.x, vv.x, a, bc1, bc2); adam_one(pv.y, gv.y, mv.y, vv.y, a, bc1, bc2);
         adam_one(pv.z, gv.z, mv.z, vv.z, a, bc1, bc2); adam_one(pv.w, gv.w, mv.w, vv.w, a, bc1, bc2);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(pv.x), fabsf(pv.y))), fmaxf(fabsf(pv.z), fabsf(pv.w)));
         *reinterpret_cast<float4 *>(p + i) = pv;
         *reinterpret_cast<float4 *>(m + i) = mv;
         *reinterpret_cast<float4 *>(v + i) = vv;
       } else {
-        for (int64_t k = i; k < n && k < i + 4; ++k) adam_one(p[k], g[k], m[k], v[k], a, bc1, bc2);
+        for (int64_t k = i; k < n && k < i + 4; ++k) { adam_one(p[k], g[k], m[k], v[k], a, bc1, bc2); amax = fmaxf(amax, fabsf(p[k])); }
       }
     }
   } else {
-    for (int64_t i = base + threadIdx.x; i < n && i < base + kChunk; i += kOT) adam_one(p[i], g[i], m[i], v[i], a, bc1, bc2);
+    for (int64_t i = base + threadIdx.x; i < n && i < base + kChunk; i += kOT) { adam_one(p[i], g[i], m[i], v[i], a, bc1, bc2); amax = fmaxf(amax, fabsf(p[i])); }
   }
+  if (a.amax[t]) {
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(a.amax[t], __float_as_uint(amax));
+  }
+ }
 }
 
 // optim.pyx:266-267: beta1_t *= beta1; beta2_t *= beta2 (Python floats = IEEE doubles)
@@ -187,7 +201,7 @@ static int adam_step_impl(int n_tensors, float *const *params, const float *cons
                           float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
                           double eps, double weight_decay, double one_minus_beta1_t,
                           double one_minus_beta2_t, int first_step, double grad_scale,
-                          const double *bias_state) {
+                          const double *bias_state, unsigned int *const *amax) {
   int rc;
   if ((rc = ensure_init())) return rc;
   SK_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || (params && grads && m && v && sizes)), "sk_adam_step: null list");
@@ -200,6 +214,7 @@ static int adam_step_impl(int n_tensors, float *const *params, const float *cons
       SK_REQUIRE(params[i] && grads[i] && m[i] && v[i] && sizes[i] >= 0, "sk_adam_step: tensor %d has a null pointer", i);
       if (sizes[i] == 0) continue;
       a.p[n] = params[i]; a.g[n] = grads[i]; a.m[n] = m[i]; a.v[n] = v[i]; a.size[n] = sizes[i];
+      a.amax[n] = amax ? amax[i] : nullptr;
       a.block_start[n] = blocks;
       blocks += (int)((sizes[i] + kChunk - 1) / kChunk);
       ++n;
@@ -217,8 +232,13 @@ static int adam_step_impl(int n_tensors, float *const *params, const float *cons
     if (blocks == 0) continue;
     double elems = 0;
     for (int k = 0; k < n; ++k) elems += (double)a.size[k];
+    a.total_blocks = blocks;
+    // SOKET_B200_OPT_GRID_CAP = blocks per SM (0 = one block per chunk): a small persistent grid leaves issue
+    // slots to the GEMMs this update overlaps with under data parallelism
+    static const int cap_env = getenv("SOKET_B200_OPT_GRID_CAP") ? atoi(getenv("SOKET_B200_OPT_GRID_CAP")) : 0;
+    const int cap = cap_env > 0 ? cap_env * ctx().num_sms : blocks;
     ProfScope ps(SK_PROF_OPTIM, elems * (first_step ? 20.0 : 28.0));
-    adam_kernel<<<blocks, kOT, 0, stream()>>>(a);
+    adam_kernel<<<blocks < cap ? blocks : cap, kOT, 0, stream()>>>(a);
     SK_LAUNCH_CHECK();
   }
   return SK_OK;
@@ -229,7 +249,16 @@ int sk_adam_step(int n_tensors, float *const *params, const float *const *grads,
                  double eps, double weight_decay, double one_minus_beta1_t,
                  double one_minus_beta2_t, int first_step, double grad_scale) {
   return adam_step_impl(n_tensors, params, grads, m, v, sizes, lr, beta1, beta2, eps, weight_decay,
-                        one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale, nullptr);
+                        one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale, nullptr, nullptr);
+}
+
+int sk_adam_step_amax(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                      float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                      double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                      const double *bias_state, int first_step, double grad_scale, unsigned int *const *amax) {
+  SK_REQUIRE(amax, "sk_adam_step_amax: null word list");
+  return adam_step_impl(n_tensors, params, grads, m, v, sizes, lr, beta1, beta2, eps, weight_decay,
+                        one_minus_beta1_t, one_minus_beta2_t, first_step, grad_scale, bias_state, amax);
 }
 
 int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *grads, float *const *m,
@@ -238,7 +267,7 @@ int sk_adam_step_dev(int n_tensors, float *const *params, const float *const *gr
                      double grad_scale) {
   SK_REQUIRE(bias_state, "sk_adam_step_dev: null bias state");
   return adam_step_impl(n_tensors, params, grads, m, v, sizes, lr, beta1, beta2, eps, weight_decay,
-                        0.0, 0.0, first_step, grad_scale, bias_state);
+                        0.0, 0.0, first_step, grad_scale, bias_state, nullptr);
 }
 
 int sk_adam_bias_advance(double *bias_state, double beta1, double beta2) {

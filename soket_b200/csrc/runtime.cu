@@ -419,14 +419,14 @@ int sk_d2d(void *dst, const void *src, size_t nbytes) {
   int rc = ensure_init();
   if (rc) return rc;
   if (nbytes == 0) return SK_OK;
-  SK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx().stream));
+  SK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx().launch));
   return SK_OK;
 }
 int sk_memset(void *dst, int byte, size_t nbytes) {
   int rc = ensure_init();
   if (rc) return rc;
   if (nbytes == 0) return SK_OK;
-  SK_CUDA(cudaMemsetAsync(dst, byte, nbytes, ctx().stream));
+  SK_CUDA(cudaMemsetAsync(dst, byte, nbytes, ctx().launch));
   return SK_OK;
 }
 

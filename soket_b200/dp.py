@@ -193,6 +193,7 @@ class DataParallel:
                 self._where[id(params[i])] = (len(self._buckets), i)
             self._buckets.append(b)
         self._ev_done = B.Event()
+        self._last_bucket = None
         E.set_leaf_grad_hook(self._on_leaf_grad)
 
     # ------------------------------------------------------------------------------------------
@@ -231,10 +232,19 @@ class DataParallel:
         b.ev_reduced.wait(B.STREAM_OPT)
         B.launch_stream(B.STREAM_OPT)
         try:
-            self.optim.update(sorted(b.seen))
+            idx = sorted(b.seen)
+            self.optim.update(idx)
+            # the updated weights' GEMM operand splits, off the critical path too: the next forward
+            # finds them cached (engine.linear -> get_split)
+            if self.E.presplit_enabled():
+                for i in idx:
+                    w = self.optim._params[i]._data
+                    if self.E.weight_split_eligible(w):
+                        B.get_split(w)
         finally:
             B.launch_stream(B.STREAM_COMPUTE)
         b.launched = True
+        self._last_bucket = b
 
     def step(self):
         """The optimizer step of a data-parallel iteration (call after `backward()`)."""
@@ -255,6 +265,11 @@ class DataParallel:
         for b in self._buckets:
             b.arrived, b.launched = 0, False
             b.seen.clear()
+
+    def timeline_events(self):
+        """(event after the last all-reduce of the step, event after the last optimizer update) --
+        recorded on the comm / optimizer streams by the most recent `step()`; for phase timing."""
+        return (self._last_bucket.ev_reduced if self._last_bucket is not None else None), self._ev_done
 
     def finish(self):
         """Kept for callers of the round-1 API (`finish(); optim.step()`): reduce whatever is

@@ -3,7 +3,10 @@ from soket_b200._core cimport ndarray
 
 
 cdef class Tensor:
-    cdef public ndarray _data
+    cdef ndarray _d                # the array, or None while the tensor is DEFERRED (lazy mode)
+    cdef public object _lz         # deferred elementwise node: (kind, op, inputs, scalar, rev) | None
+    cdef public tuple _lshape      # its shape while deferred
+    cdef public int _nuse          # deferred consumers of this deferred node
     cdef public object _dtype
     cdef public object _device
     cdef public object _grad

@@ -193,9 +193,12 @@ def cpu():
 
 
 # ---- lazy mode (tensor.pyx:24-51) -----------------------------------------------------------
-# The reference's lazy() only postpones Tensor._compute_data() until a value is needed; results
-# are the same.  This engine always evaluates at construction (an admissible schedule of the
-# same graph), so the switch is accepted and remembered but changes nothing.
+# lazy() (tensor.pyx:24-51): the reference postpones Tensor._compute_data() until a value is needed
+# (tensor.pyx:790-810); results are the same.  Here the switch opens a FUSION WINDOW: float32
+# elementwise / scalar / unary nodes created while it is on are recorded, not launched, and the whole
+# chain runs as ONE kernel (sk_ewise_fused) the moment some value is needed -- `.item()`, `.numpy()`,
+# a reduction, a matmul, backward.  Everything else evaluates at construction as before.  See
+# `_realize` below.
 _LAZY_STATE = False
 
 
@@ -561,6 +564,9 @@ cdef class Tensor:
         self._partials = None
         self._retain_grad = False
         self._grad_buf = None
+        self._lz = None
+        self._lshape = None
+        self._nuse = 0
         self._device = _default_device() if device is None else device
         if isinstance(array, Tensor):
             other = <Tensor> array
@@ -599,6 +605,53 @@ cdef class Tensor:
         t._requires_grad = requires_grad
         t._retain_grad = False
         t._grad_buf = None
+        t._lz = None
+        t._lshape = None
+        t._nuse = 0
+        return t
+
+    # ---- deferred (lazy-mode) nodes --------------------------------------------------
+    @property
+    def _data(self):
+        """The device array; a deferred node is evaluated here, with its whole pending chain."""
+        if self._d is None and self._lz is not None:
+            _realize(self)
+        return self._d
+
+    @_data.setter
+    def _data(self, value):
+        self._d = value
+        self._lz = None
+
+    @staticmethod
+    def _deferred(op, tuple inputs, tuple spec, tuple shape, dtype):
+        """tensor.pyx:1018-1070 _make_from_op in lazy mode: the node exists (shape, dtype, graph
+        links), its data does not yet."""
+        cdef Tensor t = Tensor.__new__(Tensor)
+        cdef Tensor i
+        t._d = None
+        t._dtype = dtype
+        t._device = _default_device()
+        t._grad = None
+        t._partials = None
+        t._retain_grad = False
+        t._grad_buf = None
+        t._nuse = 0
+        t._lz = spec
+        t._lshape = shape
+        t._requires_grad = False
+        t._op = None
+        t._inputs = ()
+        for x in inputs:
+            if x is not None:
+                i = <Tensor> x
+                if i._requires_grad:
+                    t._requires_grad = True
+                if i._d is None and i._lz is not None:
+                    i._nuse += 1
+        if t._requires_grad:
+            t._op = op
+            t._inputs = inputs
         return t
 
     @staticmethod
@@ -624,11 +677,17 @@ cdef class Tensor:
     @property
     def dtype(self): return self._dtype
     @property
-    def shape(self): return self._data.shape
+    def shape(self): return self._d.shape if self._d is not None else self._lshape
     @property
-    def size(self): return self._data.size
+    def size(self):
+        if self._d is not None:
+            return self._d.size
+        n = 1
+        for s in self._lshape:
+            n *= s
+        return n
     @property
-    def ndim(self): return self._data.ndim
+    def ndim(self): return self._d.ndim if self._d is not None else len(self._lshape)
     @property
     def device(self): return self._device
     @property
@@ -770,7 +829,11 @@ cdef class Tensor:
         if isinstance(other, Tensor):
             t = <Tensor> other
             dt = self._dtype if self._dtype == t._dtype else promote_types(self._dtype, t._dtype)
-            _bshape(self.shape, t.shape)
+            bs = _bshape(self.shape, t.shape)
+            if _LAZY_STATE and fn in _FUSED_BIN:
+                a, b = (t, self) if commute else (self, t)
+                if _deferrable(a, bs) and _deferrable(b, bs):
+                    return Tensor._deferred(ew_op(), (a, b), ('bin', _FUSED_BIN[fn], (a, b), None, 0), bs, dt)
             if commute:
                 return Tensor._from_op(ew_op(), (t, self), fn(t._data, self._data, dtype=dt.name), dt)
             return Tensor._from_op(ew_op(), (self, t), fn(self._data, t._data, dtype=dt.name), dt)
@@ -779,6 +842,9 @@ cdef class Tensor:
         dt = _scalar_dtype(other)
         if self._dtype != dt:
             dt = promote_types(self._dtype, dt)
+        if _LAZY_STATE and fn in _FUSED_BIN and dt.name == 'float32' and _deferrable(self, self.shape):
+            return Tensor._deferred(sc_op(other, bool(commute)), (self,),
+                                    ('sc', _FUSED_BIN[fn], (self,), float(other), 1 if commute else 0), self.shape, dt)
         if commute:
             return Tensor._from_op(sc_op(other, True), (self,), fn(other, self._data, dtype=dt.name), dt)
         return Tensor._from_op(sc_op(other, False), (self,), fn(self._data, other, dtype=dt.name), dt)
@@ -804,6 +870,8 @@ cdef class Tensor:
     def __rpow__(self, other):
         return self._binary(other, B.power, _EwisePow, _ScalarPow, True)
     def __neg__(self):
+        if _LAZY_STATE and _deferrable(self, self.shape):
+            return Tensor._deferred(_Neg(), (self,), ('un', SK_UOP_NEG, (self,), None, 0), self.shape, self._dtype)
         return Tensor._from_op(_Neg(), (self,), B.negative(self._data), self._dtype)
 
     def __matmul__(self, other):
@@ -1016,6 +1084,197 @@ cdef void _compute_gradient(Tensor root, object seed):
         g = None; grads = None
 
 
+# ============================================================================ lazy-mode fusion window
+# A deferred node records ONE float32 elementwise step:
+#   ('bin', sk_binary_op, (x, y), None, 0)        x (op) y, both tensors
+#   ('sc',  sk_binary_op, (x,), scalar, rev)      x (op) scalar, or scalar (op) x when rev
+#   ('un',  sk_unary_op,  (x,), None, 0)
+# Each operand either has the node's full shape or broadcasts against it as a last-axis vector / a
+# single element (the bias add of prototypes.pyx:113, the gamma / beta of forward.pyx:343-352, the
+# (B, 1)-free cases); anything else is evaluated eagerly, which also ends the window for its inputs.
+_FUSED_BIN = {B.add: SK_OP_ADD, B.subtract: SK_OP_SUB, B.multiply: SK_OP_MUL, B.divide: SK_OP_DIV,
+              B.power: SK_OP_POW}
+_lazy_stats = {'programs': 0, 'nodes': 0}
+
+
+def lazy_stats(reset=False):
+    """{'programs': fused launches, 'nodes': deferred nodes evaluated by them} since the last reset."""
+    out = dict(_lazy_stats)
+    if reset:
+        _lazy_stats['programs'] = 0
+        _lazy_stats['nodes'] = 0
+    return out
+
+
+cdef int _operand_kind(tuple shape, tuple full) except -2:
+    """How a tensor of `shape` reads inside a kernel over `full`: SK_F_FULL / SK_F_VECTOR / SK_F_SINGLE,
+    or -1 when it does not fit the fused kernel's indexing."""
+    cdef long n = 1
+    for s in shape:
+        n *= s
+    if shape == full:
+        return SK_F_FULL
+    if n == 1:
+        return SK_F_SINGLE
+    if len(full) >= 1 and len(shape) <= len(full) and shape[-1] == full[-1] and n == full[-1]:
+        return SK_F_VECTOR
+    return -1
+
+
+cdef bint _deferrable(Tensor t, tuple full):
+    if t._dtype.name != 'float32' or len(full) == 0:
+        return False
+    if _operand_kind(t.shape, full) < 0:
+        return False
+    if t._d is not None:
+        return t._d._code == SK_F32 and t._d._is_contiguous()
+    return t._lz is not None
+
+
+class _Overflow(Exception):
+    pass
+
+
+cdef class _Program:
+    cdef sk_fused_program p
+    cdef list keep          # input arrays stay alive until the launch is queued
+    cdef dict index
+    cdef list free_temps
+    cdef tuple full
+    cdef int nodes
+
+    def __cinit__(self):
+        self.p.n_ops = 0
+        self.p.n_in = 0
+        self.keep = []
+        self.index = {}
+        self.free_temps = [2, 1, 0]
+        self.nodes = 0
+
+    cdef int op(self, int code, int sub, int src, int idx, int rev, float cst) except -1:
+        cdef int k = self.p.n_ops
+        if k >= SK_FUSED_MAX_OPS:
+            raise _Overflow()
+        self.p.code[k] = code; self.p.sub[k] = sub; self.p.src[k] = src; self.p.idx[k] = idx
+        self.p.rev[k] = rev; self.p.cst[k] = cst
+        self.p.n_ops = k + 1
+        return 0
+
+    cdef int input(self, Tensor t) except -1:
+        """Index of a MATERIALISED operand (realising it first if it is a deferred node that cannot
+        be inlined)."""
+        cdef ndarray a = t._data
+        key = id(a)
+        if key in self.index:
+            return self.index[key]
+        cdef int k = self.p.n_in
+        if k >= SK_FUSED_MAX_INPUTS:
+            raise _Overflow()
+        if not a._is_contiguous():
+            a = a._compact()
+        self.p.inp[k] = <const float *> a._ptr
+        self.p.in_kind[k] = _operand_kind(a.shape, self.full)
+        self.p.n_in = k + 1
+        self.keep.append(a)
+        self.index[key] = k
+        return k
+
+    cdef bint inline(self, Tensor t):
+        """A deferred node is evaluated inside this program when it lives in the same index space and
+        nobody else is waiting for it; otherwise it is materialised once and read as an input."""
+        return t._d is None and t._lz is not None and t._lshape == self.full and t._nuse <= 1
+
+    cdef int emit(self, Tensor t) except -1:
+        """Leave the value of `t` in the accumulator."""
+        cdef Tensor x, y
+        cdef int tmp
+        if not self.inline(t):
+            self.op(SK_F_LOAD, 0, SK_F_IN, self.input(t), 0, 0.0)
+            return 0
+        kind, sub, ins, scalar, rev = t._lz
+        self.nodes += 1
+        if kind == 'un':
+            self.emit(<Tensor> ins[0])
+            self.op(SK_F_UN, sub, 0, 0, 0, 0.0)
+        elif kind == 'sc':
+            self.emit(<Tensor> ins[0])
+            self.op(SK_F_BIN, sub, SK_F_CONST, 0, rev, <float> scalar)
+        else:
+            x = <Tensor> ins[0]; y = <Tensor> ins[1]
+            if not self.inline(y):
+                self.emit(x)
+                self.op(SK_F_BIN, sub, SK_F_IN, self.input(y), 0, 0.0)
+            elif not self.inline(x):
+                self.emit(y)
+                self.op(SK_F_BIN, sub, SK_F_IN, self.input(x), 1, 0.0)       # x (op) acc
+            else:
+                if not self.free_temps:
+                    raise _Overflow()
+                self.emit(y)
+                tmp = self.free_temps.pop()
+                self.op(SK_F_STORE, 0, 0, tmp, 0, 0.0)
+                self.emit(x)
+                self.op(SK_F_BIN, sub, SK_F_TEMP, tmp, 0, 0.0)
+                self.free_temps.append(tmp)
+        return 0
+
+
+cdef object _split_point(Tensor t, int depth):
+    """A deferred node `depth` levels below `t` along its first pending branch (or the end of that
+    branch): materialising it cuts an over-long chain into programs of about that many steps."""
+    cdef Tensor cur = t, x
+    cdef int i
+    for i in range(depth):
+        nxt = None
+        for obj in cur._lz[2]:
+            x = <Tensor> obj
+            if x._d is None and x._lz is not None:
+                nxt = x
+                break
+        if nxt is None:
+            break
+        cur = <Tensor> nxt
+    return None if cur is t else cur
+
+
+cdef int _realize(Tensor t) except -1:
+    """Evaluate a deferred node: compile the pending elementwise subgraph hanging off it into one
+    accumulator program (tensor.pyx:790-810 does the same walk, calling the backend once per node)
+    and launch it."""
+    cdef _Program prog
+    cdef ndarray out
+    cdef int64_t shp[8]
+    cdef int i, nd = len(t._lshape)
+    while True:
+        prog = _Program()
+        prog.full = t._lshape
+        try:
+            # the root is always computed here, whatever its consumer count
+            saved = t._nuse
+            t._nuse = 0
+            try:
+                prog.emit(t)
+            finally:
+                t._nuse = saved
+            break
+        except _Overflow:
+            victim = _split_point(t, 40)
+            if victim is None:
+                raise RuntimeError('lazy evaluation: an elementwise node does not fit one fused program')
+            _realize(<Tensor> victim)
+    for i in range(nd):
+        shp[i] = t._lshape[i]
+    out = _new_array(nd, shp, SK_F32)
+    prog.p.n = out._numel()
+    prog.p.cols = t._lshape[nd - 1] if nd else 1
+    _check(sk_ewise_fused(&prog.p, <float *> out._ptr))
+    _lazy_stats['programs'] += 1
+    _lazy_stats['nodes'] += prog.nodes
+    t._d = out
+    t._lz = None
+    return 0
+
+
 # ============================================================================ creation fns
 def _mk(ndarray data, dtype, requires_grad):
     return Tensor._const(data, dtype, bool(requires_grad))
@@ -1098,10 +1357,14 @@ def stack(tensors, axis=0):
 
 # soket/tensor/detached.pyx:8-79
 def log(Tensor x):
+    if _LAZY_STATE and _deferrable(x, x.shape):
+        return Tensor._deferred(_Log(), (x,), ('un', SK_UOP_LOG, (x,), None, 0), x.shape, x._dtype)
     return Tensor._from_op(_Log(), (x,), B.log(x._data), x._dtype)
 
 
 def exp(Tensor x):
+    if _LAZY_STATE and _deferrable(x, x.shape):
+        return Tensor._deferred(_Exp(), (x,), ('un', SK_UOP_EXP, (x,), None, 0), x.shape, x._dtype)
     return Tensor._from_op(_Exp(), (x,), B.exp(x._data), x._dtype)
 
 
@@ -1138,6 +1401,13 @@ cdef inline bint _presplit_shapes(ndarray xd, ndarray wd):
         return False
     cdef int64_t Bn = xd._shape[0], I = xd._shape[1], O = wd._shape[1]
     return Bn >= 256 and I >= 256 and O >= 128 and I % 8 == 0 and O % 8 == 0 and wd._is_contiguous()
+
+
+def weight_split_eligible(w):
+    """Would `linear` consume this weight array through the pre-split path (for some batch >= 256)?"""
+    cdef ndarray wd = <ndarray> w
+    return (wd._ndim == 2 and wd._code == SK_F32 and wd._shape[0] >= 256 and wd._shape[1] >= 128
+            and wd._shape[0] % 8 == 0 and wd._shape[1] % 8 == 0 and wd._is_contiguous())
 
 
 cdef object _take_sole_partial(Tensor x):
@@ -1467,6 +1737,8 @@ class _AddReluOp(Op):
 
 def relu_(Tensor x):
     """soket/nn/prototypes.pyx:302-311."""
+    if _LAZY_STATE and _deferrable(x, x.shape):
+        return Tensor._deferred(_Relu(), (x,), ('un', SK_UOP_RELU, (x,), None, 0), x.shape, x._dtype)
     return Tensor._from_op(_Relu(), (x,), B.maximum(x._data, 0), x._dtype)
 
 

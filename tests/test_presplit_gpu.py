@@ -40,17 +40,19 @@ def test_gemm_on_presplit_operands_all_orientations(sk, M, K, N):
 
 def test_split_reconstructs_and_pads(sk):
     rng = np.random.default_rng(0)
-    x = (rng.standard_normal((300, 203)) * np.exp(rng.standard_normal((300, 1)) * 3)).astype("float32")
+    x = (rng.standard_normal((300, 204)) * np.exp(rng.standard_normal((300, 1)) * 3)).astype("float32")
     m = sk.split_f16(sk.array(x))
-    assert (m.rows, m.cols, m.ld) == (300, 203, 208)
+    assert (m.rows, m.cols, m.ld) == (300, 204, 208)
     hi, lo, sc = sk.asnumpy(m.hi).astype(np.float64), sk.asnumpy(m.lo).astype(np.float64), sk.asnumpy(m.scale)
     amax = float(np.abs(x).max())
     assert sc[2] == np.float32(amax) and sc[0] * sc[1] == 1.0
     assert 2.0 ** 14 <= amax * sc[0] < 2.0 ** 15                           # top of the fp16 range, one bit of headroom
-    assert np.all(hi[:, 203:] == 0) and np.all(lo[:, 203:] == 0)          # K padding contributes nothing
-    rec = (hi[:, :203] + lo[:, :203]) / sc[0]
+    assert np.all(hi[:, 204:] == 0) and np.all(lo[:, 204:] == 0)          # K padding contributes nothing
+    rec = (hi[:, :204] + lo[:, :204]) / sc[0]
     # 22 significant bits, or an absolute 2^-25 of a scaled unit for elements far below the maximum
     assert np.all(np.abs(rec - x) <= 2.0 ** -22 * np.abs(x) + 2.0 ** -25 / sc[0])
+    with pytest.raises(ValueError):
+        sk.split_f16(sk.array(x[:, :203]))                                  # rows must start 16-byte aligned
     # the bias gradient rides along
     m2, cs = sk.split_f16(sk.array(x), True)
     assert np.array_equal(sk.asnumpy(m2.hi), sk.asnumpy(m.hi))
