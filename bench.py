@@ -207,7 +207,7 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def workload_config(args, world, per_gpu, impl="ours"):
+def workload_config(args, world, per_gpu):
     trainable = (4 + 8 * args.blocks) if not args.verbatim_q1 else 4
     cfg = {
         "workload": f"MLPResNet(784, hidden={args.hidden}, blocks={args.blocks}, classes=10, "
@@ -218,8 +218,6 @@ def workload_config(args, world, per_gpu, impl="ours"):
         "parallelism": f"dp{world}" if world > 1 else "single",
         "l2": "per-step working set (activations + 1.09 GB of weights) >> 126 MB L2; no explicit flush",
     }
-    if impl == "reference":
-        cfg["cpu_sample_rows_per_step"] = args.cpu_sample_batch
     return cfg
 
 
@@ -294,9 +292,12 @@ def run_reference(args, env):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, args.global_batch, "reference"),
+        # the SAME workload description as this repo's arm at this N (the driver compares them); what the
+        # CPU actually steps through per timed step -- a bounded sample of it -- is in cpu_baseline
+        "config": workload_config(args, max(args.gpus, 1),
+                                  args.global_batch // max(args.gpus, 1) if args.scaling == "strong" else args.global_batch),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": ref.cores, "kind": ref.kind,
-                         "blas_threads": blas_threads(),
+                         "blas_threads": blas_threads(), "rows_per_step": sample,
                          "env": {k: os.environ.get(k) for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS")},
                          "sample": f"{args.steps} Adam step(s) of the same model on {sample} rows per step after "
                                    f"{args.warmup} warm-up step(s) (the full batch is {args.global_batch} rows: "

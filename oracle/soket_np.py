@@ -436,9 +436,13 @@ class MLPResNet:
         ln = self.norm == "layer"
         axes = (1,) if ln else (0,)
         G = {}
+        # tests only: the adjoint each Linear's matmul received, by layer name (with the layer inputs on
+        # the tape this gives the fp32 GEMM error bound 1e-5 (|in|.T @ |adj|) of every weight gradient)
+        A = self.adj_mm = {}
         adj = sxent_bwd(np.ones((), F32), T["logits"], self.onehot)
         # logits = h @ out.W + out.b
         g_mm, g_b = add_bwd(adj)
+        A["out"] = g_mm
         G["out.b"] = broadcast_grad(g_b, P["out.b"].shape)
         dh, G["out.W"] = matmul_bwd(g_mm, T["out.in"], P["out.W"])
         B = T["X"].shape[0]
@@ -451,12 +455,14 @@ class MLPResNet:
                 d_fn, P[f"blk{i}.n2.g"], blk["n2.xs"], blk["n2.r"], blk["n2.norm"], axes, obs, ln)
             g_mm, g_b = add_bwd(dz)
             G[f"blk{i}.lin2.b"] = broadcast_grad(g_b, P[f"blk{i}.lin2.b"].shape)
+            A[f"blk{i}.lin2"] = g_mm
             da, G[f"blk{i}.lin2.W"] = matmul_bwd(g_mm, blk["lin2.in"], P[f"blk{i}.lin2.W"])
             da = relu_back(blk["relu1.in"], da, 1 + 2 * i)
             dz, G[f"blk{i}.n1.g"], G[f"blk{i}.n1.b"] = norm_bwd(
                 da, P[f"blk{i}.n1.g"], blk["n1.xs"], blk["n1.r"], blk["n1.norm"], axes, obs, ln)
             g_mm, g_b = add_bwd(dz)
             G[f"blk{i}.lin1.b"] = broadcast_grad(g_b, P[f"blk{i}.lin1.b"].shape)
+            A[f"blk{i}.lin1"] = g_mm
             dx1, G[f"blk{i}.lin1.W"] = matmul_bwd(g_mm, blk["in"], P[f"blk{i}.lin1.W"])
             # block input has two partial adjoints, summed in list order
             # (autodiff.pyx:30-41): the Residual add's copy first, then Linear1's dX
@@ -464,6 +470,7 @@ class MLPResNet:
         d = relu_back(T["lin0.pre"], dh, 0)
         g_mm, g_b = add_bwd(d)
         G["lin0.b"] = broadcast_grad(g_b, P["lin0.b"].shape)
+        A["lin0"] = g_mm
         _, G["lin0.W"] = matmul_bwd(g_mm, T["X"], P["lin0.W"], need_dx=False)
         self.grads = G
         return G

@@ -1428,6 +1428,17 @@ def new_absmax_word(ndarray owner=None):
     return a
 
 
+def has_absmax(ndarray x):
+    """Does x carry a |max| word that is still valid for its contents (so that split_f16 needs no
+    temporary of its own -- a requirement for running it off the compute stream)?"""
+    cdef AbsMax am
+    if not isinstance(x._meta, AbsMax):
+        return False
+    am = <AbsMax> x._meta
+    return (am.version == x._buf.version and am.epoch == _GRAPH_EPOCH
+            and (am.capture == 0 or am.capture == _capture_now()))
+
+
 def bind_absmax_word(ndarray word, ndarray x):
     """Attach a device word a kernel has filled with the bit pattern of max |x| to x."""
     cdef AbsMax a = AbsMax.__new__(AbsMax)

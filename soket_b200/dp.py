@@ -239,7 +239,10 @@ class DataParallel:
             if self.E.presplit_enabled():
                 for i in idx:
                     w = self.optim._params[i]._data
-                    if self.E.weight_split_eligible(w):
+                    # only with the |max| the optimizer kernel left behind: the split then needs no
+                    # scratch allocation, which the stream-ordered allocator could hand to the
+                    # compute stream while this stream still uses it
+                    if self.E.weight_split_eligible(w) and B.has_absmax(w):
                         B.get_split(w)
         finally:
             B.launch_stream(B.STREAM_COMPUTE)
