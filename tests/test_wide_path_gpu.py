@@ -12,11 +12,12 @@ ran.
 Reference semantics: examples/mlp_resnet/model.py:40-58,72-95, soket/tensor/ops/forward.pyx:172-178,
 backward.pyx:704-742.  Bars (north_star): 1e-5 relative per fp32 op result -- here per training
 step with both sides started from identical state (teacher forcing): the loss at 1e-5, every gradient
-tensor at 1e-5 in the rms sense (||err|| <= 1e-5 ||want||), and element-wise: weight gradients
-dW = in.T @ adj at the fp32 GEMM bound the kernel tests use, |err| <= 1e-5 |want| + 1e-5 (|in|.T @ |adj|)
-(an element is a sum of `batch` products of either sign: its error is set by the size of the terms;
-the classical bound for a K = 1024 fp32 dot product is 6e-5 of that sum), vector gradients at
-|err| <= 2e-5 |want| + 4e-5 rms -- and 1e-4 on the loss at the end of a
+tensor at 1e-5 in the rms sense (||err|| <= 1e-5 ||want||), and element-wise
+|err| <= 2e-5 |want| + 4e-5 rms(want) for what the adjoint reaching a layer has accumulated on its way
+down (16 GEMMs and 16 LayerNorm backwards for the first block) plus, for weight gradients
+dW = in.T @ adj, the fp32 GEMM bound of the kernel tests, 1e-5 (|in|.T @ |adj|) (an element is a sum of
+`batch` products of either sign: its rounding is set by the size of the terms; the classical bound for
+a K = 1024 fp32 dot product is 6e-5 of that sum) -- and 1e-4 on the loss at the end of a
 free-running run on top of what the CPU path does to itself under a 1e-7 perturbation.
 """
 import numpy as np
@@ -182,15 +183,18 @@ def test_wide_model_50_steps_teacher_forced(sk, opt):
                 rr = rms_rel_err(grads[k], g)
                 worst_rms = max(worst_rms, rr)
                 assert rr <= 1e-5, (s, k, rr)
+            # element-wise: |err| <= PROPAGATED + LOCAL.  Propagated: the adjoint reaching this layer is the
+            # composite of up to ~50 fp32 op results (16 GEMMs and 16 LayerNorm backwards deep), each at
+            # 1e-5 of its own scale -> 2e-5 |want| + 4e-5 rms(want).  Local (weights): dW = in.T @ adj is a
+            # sum of `batch` products of either sign, rounded at the size of the TERMS -> the kernel
+            # tests' fp32 GEMM bound 1e-5 (|in|.T @ |adj|).
+            bound = 2e-5 * np.abs(g) + 4e-5 * max(float(np.sqrt(np.mean(g.astype(np.float64) ** 2))), 1e-30) + 1e-7 * gscale
             if k.endswith(".W"):
-                # element-wise at the fp32 GEMM bound: dW = in.T @ adj, |err| <= 1e-5 (|want| + |in|.T @ |adj|)
                 lay = k[:-2]
                 xin = (om.tape["X"] if lay == "lin0" else om.tape["out.in"] if lay == "out"
                        else om.tape[lay.split(".")[0]]["in" if lay.endswith("lin1") else "lin2.in"])
-                terms = np.abs(xin).T @ np.abs(om.adj_mm[lay])
-                ex = float((np.abs(grads[k].astype(np.float64) - g) / (1e-5 * (np.abs(g) + terms) + 1e-30)).max())
-            else:
-                ex = elementwise_excess(grads[k], g, rtol=2e-5, floor_frac=4e-5, abs_floor=1e-7 * gscale)
+                bound = bound + 1e-5 * (np.abs(xin).T @ np.abs(om.adj_mm[lay]))
+            ex = float((np.abs(grads[k].astype(np.float64) - g) / bound).max())
             worst_grad = max(worst_grad, ex)
             assert ex <= 1.0, (s, k, ex)
             if opt == "sgd":
