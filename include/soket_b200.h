@@ -425,6 +425,28 @@ int sk_adam_step_amax(int n_tensors, float *const *params, const float *const *g
                       float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
                       double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
                       const double *bias_state, int first_step, double grad_scale, unsigned int *const *amax);
+/* sk_adam_step_amax with PERSISTENT |max| words and, optionally, the new weights' fp16x3 operand split
+ * written by the same kernel (replaces the weight's own sk_split_f16 pass after every step:
+ * 4 B/element of extra writes instead of an 8 B/element pass).
+ *   amax2   device uint32[2] per tensor (NULL: tensor not tracked): [0] = bit pattern of max |p| BEFORE
+ *           the update (0 = unknown: only allowed without hi), [1] = 0.  After the launch [0] holds
+ *           max |p_new| and [1] is 0 again, so the same words serve the next step (and a CUDA-graph replay).
+ *   hi, lo  fp16 arrays of `size` elements or NULL; scale4 = float[4] {scale, 1/scale, bound, 0}:
+ *           p_new * scale = hi + lo, scale = the power of two sk_split_f16 would pick for
+ *           bound = max |p_old| + update_bound -- chosen before any element is updated.
+ *   update_bound  a bound of |p_new - p_old| that holds for EVERY element whatever the gradients:
+ *           lr * max_t |m_hat / sqrt(v_hat)| <= lr * (1-b1)/sqrt(1-b2) * sqrt(sum_k (b1^2/b2)^k) *
+ *           sqrt(1-b2^t)/(1-b1^t) (Cauchy-Schwarz on the two moving averages; optim.pyx:224-263). */
+typedef struct {
+    unsigned int *amax2;
+    void *hi, *lo;
+    float *scale4;
+} sk_adam_split;
+int sk_adam_step_split(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                       float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                       const double *bias_state, int first_step, double grad_scale, const sk_adam_split *splits,
+                       double update_bound);
 int sk_adam_bias_advance(double *bias_state, double beta1, double beta2);
 
 /* ------------------------------------------------------------- data parallel

@@ -244,6 +244,16 @@ cdef extern from "soket_b200.h" nogil:
                           float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
                           double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
                           const double *bias_state, int first_step, double grad_scale, unsigned int *const *amax)
+    ctypedef struct sk_adam_split:
+        unsigned int *amax2
+        void *hi
+        void *lo
+        float *scale4
+    int sk_adam_step_split(int n_tensors, float *const *params, const float *const *grads, float *const *m,
+                           float *const *v, const int64_t *sizes, double lr, double beta1, double beta2,
+                           double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                           const double *bias_state, int first_step, double grad_scale,
+                           const sk_adam_split *splits, double update_bound)
     int sk_adam_bias_advance(double *bias_state, double beta1, double beta2)
 
     int sk_nccl_available()

@@ -41,6 +41,7 @@ cdef class SplitMat:
     cdef long version
     cdef long epoch
     cdef long capture
+    cdef public object amax     # AbsMax (rotating words) kept alive for the optimizer's fused re-split, or None
     cdef bint valid_for(self, ndarray x)
 
 
@@ -50,11 +51,15 @@ cdef class AbsMax:
     cdef long version
     cdef long epoch
     cdef long capture
+    # two persistent words {max |x|, accumulator}: the optimizer kernel rotates them itself every step
+    # (sk_adam_step_split), so they also describe the array after the NEXT in-place update
+    cdef public bint rotating
 
 
 cdef ndarray _new_array(int ndim, const int64_t *shape, int code)
 cdef SplitMat _new_split(int64_t rows, int64_t cols)
 cdef void _bind_split(SplitMat m, ndarray x)
+cdef AbsMax _new_rotating_absmax()
 cdef long _graph_epoch()
 cdef ndarray _as_device(object x)
 cdef int _check(int rc) except -1

@@ -1406,6 +1406,7 @@ cdef SplitMat _new_split(int64_t rows, int64_t cols):
     shp[0] = 4
     m.scale = _new_array(1, shp, SK_F32)
     m.src_ptr = 0; m.version = -1; m.epoch = -1; m.capture = 0
+    m.amax = None
     return m
 
 
@@ -1425,7 +1426,23 @@ def new_absmax_word(ndarray owner=None):
     a.word = _new_array(1, &one, SK_U32)
     _check(sk_memset(<void *> a.word._ptr, 0, 4))
     a.version = -1; a.epoch = -1; a.capture = 0
+    a.rotating = False
     return a
+
+
+cdef AbsMax _new_rotating_absmax():
+    """{max |x| (0 = not known yet), accumulator}: the words sk_adam_step_split keeps current by itself."""
+    cdef AbsMax a = AbsMax.__new__(AbsMax)
+    cdef int64_t two = 2
+    a.word = _new_array(1, &two, SK_U32)
+    _check(sk_memset(<void *> a.word._ptr, 0, 8))
+    a.version = -1; a.epoch = -1; a.capture = 0
+    a.rotating = True
+    return a
+
+
+def new_rotating_absmax():
+    return _new_rotating_absmax()
 
 
 def has_absmax(ndarray x):
@@ -1443,6 +1460,7 @@ def bind_absmax_word(ndarray word, ndarray x):
     """Attach a device word a kernel has filled with the bit pattern of max |x| to x."""
     cdef AbsMax a = AbsMax.__new__(AbsMax)
     a.word = word
+    a.rotating = False
     bind_absmax(a, x)
 
 
@@ -1465,12 +1483,14 @@ def split_f16(x, want_colsum=False, out_colsum=None):
         raise ValueError('split_f16: the row length must be a multiple of 4 elements (16-byte aligned rows)')
     cdef SplitMat m = _new_split(a._shape[0], a._shape[1])
     cdef const unsigned int *amax = NULL
-    cdef AbsMax am
+    cdef AbsMax am = None
     if isinstance(a._meta, AbsMax):
         am = <AbsMax> a._meta
         if (am.version == a._buf.version and am.epoch == _GRAPH_EPOCH
                 and (am.capture == 0 or am.capture == _capture_now())):
             amax = <const unsigned int *> am.word._ptr
+        else:
+            am = None
     cdef ndarray cs = None
     cdef int64_t cols = a._shape[1]
     if want_colsum:
@@ -1485,6 +1505,8 @@ def split_f16(x, want_colsum=False, out_colsum=None):
                         amax, <void *> m.hi._ptr, <void *> m.lo._ptr, m.ld, <float *> m.scale._ptr,
                         <float *> cs._ptr if cs is not None else NULL))
     _bind_split(m, a)
+    if am is not None and am.rotating:
+        m.amax = am            # the optimizer refreshes hi / lo itself from now on (sk_adam_step_split)
     if want_colsum:
         return m, cs
     return m

@@ -318,48 +318,77 @@ def adam_bias_advance(ndarray state, double beta1, double beta2):
 
 def adam_step(list params, list grads, list m, list v, double lr, double beta1, double beta2,
               double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
-              bint first_step, double grad_scale=1.0, bias_state=None, bint emit_absmax=True):
+              bint first_step, double grad_scale=1.0, bias_state=None, bint emit_absmax=True,
+              double update_bound=-1.0):
     """In-place Adam over all tensors in ONE launch (optim.pyx:201-269).  With `bias_state`
     (device float64 {beta1^t, beta2^t}) the kernel forms the bias corrections itself and the
-    two host scalars are ignored (graph-capturable form)."""
+    two host scalars are ignored (graph-capturable form).
+
+    Weight matrices a Linear layer consumes through the fp16x3 GEMM (`_wants_amax`) carry two
+    persistent device words {max |w|, accumulator} that the kernel keeps current; once such a weight
+    also has a valid operand split (SplitMat) and `update_bound` >= 0 bounds |w_new - w_old|, the
+    kernel rewrites that split in place (sk_adam_step_split) and the weight is never split by a
+    pass of its own again."""
     cdef int n = len(params), i
     cdef _PtrLists L = _PtrLists(n)
     cdef ndarray p, g
+    cdef list wanted = []
+    cdef list fused = [None] * n          # SplitMat to refresh in the kernel
+    cdef list words = [None] * n          # AbsMax (rotating) per tracked tensor
+    cdef SplitMat sm
+    cdef AbsMax am
     for i in range(n):
         p = <ndarray> params[i]; g = <ndarray> grads[i]
         if p._numel() != g._numel():
             raise ValueError(f'adam_step: parameter {i} and its gradient differ in size')
+        if emit_absmax and _wants_amax(p):
+            # looked at BEFORE p._touch(): does the derived data describe the weights as they are now?
+            am = None
+            if isinstance(p._meta, SplitMat):
+                sm = <SplitMat> p._meta
+                if sm.amax is not None and sm.valid_for(p):
+                    am = <AbsMax> sm.amax
+                    if (update_bound >= 0.0 and sm.ld == sm.cols and p._is_contiguous()
+                            and p._numel() % 4 == 0 and (<size_t> p._ptr) % 16 == 0):
+                        fused[i] = sm
+            elif isinstance(p._meta, AbsMax) and (<AbsMax> p._meta).rotating and _B.has_absmax(p):
+                am = <AbsMax> p._meta
+            if am is None:
+                am = _B.new_rotating_absmax()
+            words[i] = am
+            wanted.append(i)
         p._touch()
         L.p[i] = _fptr(p); L.g[i] = _fptr(g)
         L.m[i] = _fptr(<ndarray> m[i]); L.v[i] = _fptr(<ndarray> v[i])
         L.sizes[i] = p._numel()
-    # weight matrices a Linear layer will re-split for its GEMMs get the |max| of their NEW values as a
-    # by-product (one zeroed word each; see sk_adam_step_amax)
-    cdef list wanted = [i for i in range(n) if _wants_amax(<ndarray> params[i])]
-    cdef unsigned int **aw = NULL
-    cdef ndarray words = None
-    cdef int64_t nw
-    cdef int k
-    if wanted and emit_absmax:
-        nw = len(wanted)
-        words = _new_array(1, &nw, SK_U32)
-        _check(sk_memset(<void *> words._ptr, 0, <size_t> nw * 4))
-        aw = <unsigned int **> malloc(n * sizeof(unsigned int *))
-        if aw == NULL:
+    cdef sk_adam_split *sp = NULL
+    if wanted:
+        sp = <sk_adam_split *> malloc(n * sizeof(sk_adam_split))
+        if sp == NULL:
             raise MemoryError()
         for i in range(n):
-            aw[i] = NULL
-        for k, i in enumerate(wanted):
-            aw[i] = (<unsigned int *> words._ptr) + k
+            sp[i].amax2 = NULL; sp[i].hi = NULL; sp[i].lo = NULL; sp[i].scale4 = NULL
+        for i in wanted:
+            am = <AbsMax> words[i]
+            sp[i].amax2 = <unsigned int *> am.word._ptr
+            if fused[i] is not None:
+                sm = <SplitMat> fused[i]
+                sp[i].hi = <void *> sm.hi._ptr
+                sp[i].lo = <void *> sm.lo._ptr
+                sp[i].scale4 = <float *> sm.scale._ptr
         try:
-            _check(sk_adam_step_amax(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
-                                     one_minus_beta1_t, one_minus_beta2_t,
-                                     _bias_ptr(<ndarray> bias_state) if bias_state is not None else NULL,
-                                     first_step, grad_scale, aw))
+            _check(sk_adam_step_split(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,
+                                      one_minus_beta1_t, one_minus_beta2_t,
+                                      _bias_ptr(<ndarray> bias_state) if bias_state is not None else NULL,
+                                      first_step, grad_scale, sp, update_bound if update_bound >= 0.0 else 0.0))
         finally:
-            free(aw)
-        for k, i in enumerate(wanted):
-            _B.bind_absmax_word(words[k:k + 1], <ndarray> params[i])
+            free(sp)
+        for i in wanted:
+            p = <ndarray> params[i]
+            if fused[i] is not None:
+                _bind_split(<SplitMat> fused[i], p)      # hi / lo now describe the NEW weights
+            else:
+                _B.bind_absmax(<AbsMax> words[i], p)
         return
     if bias_state is not None:
         _check(sk_adam_step_dev(n, L.p, L.g, L.m, L.v, L.sizes, lr, beta1, beta2, eps, weight_decay,

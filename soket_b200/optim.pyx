@@ -83,6 +83,42 @@ cdef class SGD(Optimizer):
         F.sgd_step(ps, gs, lr, self._weight_decay if self._have_weight_decay else 0.0, self.grad_scale)
 
 
+_RATIO_SUP = {}
+_FUSED_WEIGHT_SPLIT = True
+
+
+def set_fused_weight_split(on):
+    """Adam refreshes each Linear weight's fp16x3 operand split inside its own kernel (default on)."""
+    global _FUSED_WEIGHT_SPLIT
+    _FUSED_WEIGHT_SPLIT = bool(on)
+
+
+def adam_ratio_bound(beta1, beta2, t=None):
+    """An upper bound of |m_hat / sqrt(v_hat)| at step t (t=None: over every t) whatever the gradients
+    were.  With m_t = (1-b1) sum_k b1^k g_{t-k} and v_t = (1-b2) sum_k b2^k g_{t-k}^2 (optim.pyx:224-247),
+    Cauchy-Schwarz gives |m_t| <= (1-b1) sqrt(sum_{k<t} (b1^2/b2)^k) sqrt(v_t / (1-b2)); the bias
+    corrections contribute sqrt(1-b2^t) / (1-b1^t).  Returns None when no finite bound is available."""
+    b1, b2 = float(beta1), float(beta2)
+    if not (0.0 <= b1 < 1.0 and 0.0 < b2 < 1.0):
+        return None
+    q = b1 * b1 / b2
+
+    def at(n):
+        s = float(n) if q == 1.0 else (1.0 - q ** n) / (1.0 - q)
+        return (1.0 - b1) / np.sqrt(1.0 - b2) * np.sqrt(s) * np.sqrt(1.0 - b2 ** n) / (1.0 - b1 ** n)
+    if t is not None:
+        return float(at(int(t)))
+    if q >= 1.0:
+        return None                       # grows with t
+    key = (b1, b2)
+    if key not in _RATIO_SUP:
+        n = np.arange(1, 200001, dtype=np.float64)
+        sup = float(np.max((1.0 - b1) / np.sqrt(1.0 - b2) * np.sqrt((1.0 - q ** n) / (1.0 - q))
+                           * np.sqrt(1.0 - b2 ** n) / (1.0 - b1 ** n)))
+        _RATIO_SUP[key] = max(sup, (1.0 - b1) / np.sqrt(1.0 - b2) / np.sqrt(1.0 - q))   # and the t -> inf limit
+    return _RATIO_SUP[key]
+
+
 cdef class Adam(Optimizer):
     """soket/optim.pyx:134-269."""
     cdef public object _lr, _beta1, _beta2, _eps, _weight_decay
@@ -139,6 +175,10 @@ cdef class Adam(Optimizer):
             self._u[i] = B.empty(ps[k].shape, 'float32')
             self._v[i] = B.empty(ps[k].shape, 'float32')
         wd = self._weight_decay if self._have_weight_decay else 0.0
+        # |w_new - w_old| <= lr * |m_hat / (sqrt(v_hat) + eps)| <= lr * ratio bound: lets the kernel pick the
+        # scale of the new weights' fp16x3 operand split before it has seen them (sk_adam_step_split)
+        rb = adam_ratio_bound(self._beta1, self._beta2, None if self._capturable else self._t)
+        ub = -1.0 if (rb is None or not _FUSED_WEIGHT_SPLIT) else abs(float(self._lr)) * rb * 1.0001
         for group, first in ((fresh, True), (seen, False)):
             if not group:
                 continue
@@ -146,7 +186,7 @@ cdef class Adam(Optimizer):
                         [self._u[idx[k]] for k in group], [self._v[idx[k]] for k in group],
                         self._lr, self._beta1, self._beta2, self._eps, wd,
                         self._one_minus_beta1_t, self._one_minus_beta2_t, first, self.grad_scale,
-                        self._bias_dev)
+                        self._bias_dev, True, ub)
 
     def end_step(self):
         if self._capturable:

@@ -147,3 +147,26 @@ def test_gradient_arena_plan_reverse_order_aligned_buckets():
     # degenerate inputs
     assert plan_arena([], 1024) == ([], 0, [])
     assert plan_arena([5], 1 << 30) == ([0], SLOT_ALIGN, [(0, SLOT_ALIGN, [0])])
+
+
+def test_adam_ratio_bound_is_a_bound():
+    """|m_hat / sqrt(v_hat)| of Adam never exceeds adam_ratio_bound, whatever the gradient sequence
+    (here: adversarial ones -- constant, alternating, one spike, growing, shrinking)."""
+    from soket_b200.optim import adam_ratio_bound
+    for b1, b2 in [(0.9, 0.999), (0.5, 0.9), (0.0, 0.99), (0.95, 0.95)]:
+        sup = adam_ratio_bound(b1, b2)
+        T = 400
+        seqs = [np.ones(T), (-1.0) ** np.arange(T), np.r_[np.zeros(T - 1) + 1e-8, 1.0], 1.1 ** np.arange(T),
+                0.9 ** np.arange(T), np.r_[1.0, np.zeros(T - 1) + 1e-12]]
+        # the maximiser of the Cauchy-Schwarz step: g_{t-k} proportional to (b1 / b2)^k
+        seqs.append((b1 / b2) ** np.arange(T)[::-1] if b1 > 0 else np.ones(T))
+        for g in seqs:
+            m = v = 0.0
+            for t, gt in enumerate(g, 1):
+                m = b1 * m + (1 - b1) * gt
+                v = b2 * v + (1 - b2) * gt * gt
+                r = abs(m / (1 - b1 ** t)) / np.sqrt(v / (1 - b2 ** t))
+                assert r <= adam_ratio_bound(b1, b2, t) * (1 + 1e-9), (b1, b2, t, r)
+                if sup is not None:
+                    assert r <= sup * (1 + 1e-9)
+    assert adam_ratio_bound(0.9, 1.0) is None and adam_ratio_bound(0.999, 0.9) is None

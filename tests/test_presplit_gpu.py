@@ -214,3 +214,47 @@ def test_model_trains_to_the_same_numbers_with_and_without_presplit(sk, opt):
     if opt == "sgd":
         for k in p1:
             assert float(np.abs(p1[k] - p0[k]).max()) <= 1e-6 * max(float(np.abs(p0[k]).max()), 1e-30), k
+
+
+def test_adam_rewrites_the_weight_split_in_its_own_kernel(sk):
+    """sk_adam_step_split: from the second step on, the optimizer kernel leaves the new weights' hi / lo
+    next to the weights themselves (scale chosen a priori from max |w_old| + lr * ratio bound), the
+    split stays bound to the weight array, reconstructs it to 22 bits, and feeds the GEMM the very
+    bits a fresh sk_split_f16 pass would; the update itself is unchanged (bit-identical weights with
+    the fusion off)."""
+    from soket_b200 import _fused as F
+    from soket_b200 import optim as OPT
+    rng = np.random.default_rng(5)
+    w0 = (rng.standard_normal((512, 384)) * 0.05).astype("float32")
+    x = sk.array(rng.standard_normal((256, 512)).astype("float32"))
+    sx = sk.split_f16(x)
+    grads = [(rng.standard_normal((512, 384)) * 10.0 ** rng.integers(-6, 1)).astype("float32") for _ in range(6)]
+
+    def run(fused):
+        w = sk.array(w0)
+        m, v = sk.empty((512, 384), "float32"), sk.empty((512, 384), "float32")
+        b1, b2, lr = 0.9, 0.999, 1e-3
+        b1t, b2t = b1, b2
+        outs, launches = [], []
+        for t, g in enumerate(grads, 1):
+            ub = abs(lr) * OPT.adam_ratio_bound(b1, b2, t) * 1.0001 if fused else -1.0
+            F.adam_step([w], [sk.array(g)], [m], [v], lr, b1, b2, 1e-8, 0.0, 1.0 - b1t, 1.0 - b2t, t == 1, 1.0, None, True, ub)
+            b1t *= b1; b2t *= b2
+            n0 = sk.launch_count()
+            sw = sk.get_split(w)
+            launches.append(sk.launch_count() - n0)
+            outs.append((sk.asnumpy(w), sk.asnumpy(sk.gemm_split(sx, False, sw, False)), sk.asnumpy(sw.hi).astype(np.float64),
+                         sk.asnumpy(sw.lo).astype(np.float64), sk.asnumpy(sw.scale)))
+        return outs, launches
+    fused, lf = run(True)
+    plain, lp = run(False)
+    assert lf[0] >= 1 and all(n == 0 for n in lf[1:]), lf     # step 1 has no split to refresh yet; then no pass at all
+    assert all(n >= 1 for n in lp), lp
+    for (wf, yf, hi, lo, sc), (wp, yp, _, _, scp) in zip(fused, plain):
+        assert np.array_equal(wf, wp)                                       # the update is the same arithmetic
+        assert np.array_equal(yf, yp)                                       # a power-of-two scale only moves exponents
+        amax = float(np.abs(wf).max())
+        assert sc[0] * sc[1] == 1.0 and amax <= sc[2] and amax * sc[0] < 2.0 ** 15   # the a-priori bound held
+        assert sc[2] <= 1.5 * amax + 1e-2                                   # and is not wildly loose (lr * 7.3 of slack)
+        rec = (hi + lo) / sc[0]
+        assert np.all(np.abs(rec - wf) <= 2.0 ** -22 * np.abs(wf) + 2.0 ** -25 / sc[0])
