@@ -12,6 +12,8 @@ from __future__ import annotations
 import os
 import sys
 
+import numpy as np
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
@@ -101,3 +103,49 @@ def to_numpy(soket, t):
     view = soket.Tensor.from_numpy(buf)
     view[tuple(slice(None) for _ in t.shape)] = t
     return buf
+
+
+# --- ReLU sign patterns: comparing both backends at one and the same point of the derivative ---------
+
+def device_relu_signs(model, X, blocks):
+    """The sign pattern of every ReLU input of the FUSED forward (y > 0 <=> pre-activation > 0), read
+    off the fused kernels' own outputs through Sequential._run prefixes."""
+    import soket_b200.api as soket                # the device side of the comparison (tests / DP parity worker)
+    signs = []
+    h = model._run(soket.Tensor(X), 2)                       # relu(lin0(X)): GEMM with bias+ReLU epilogue
+    signs.append(h.numpy() > 0)
+    mods = list(model._storage)
+    for i in range(blocks):
+        blk = mods[2 + i]
+        r1 = blk.fn._run(h, 3)                               # relu(LN1(lin1(h))): LN kernel, ReLU epilogue
+        signs.append(r1.numpy() > 0)
+        h = blk(h)                                           # relu(h + LN2(...)): LN kernel, residual epilogue
+        signs.append(h.numpy() > 0)
+    return signs
+
+
+def oracle_relu_signs(om, blocks):
+    T = om.tape
+    out = [T["lin0.pre"] > 0]
+    for i in range(blocks):
+        out += [T[f"blk{i}"]["relu1.in"] > 0, T[f"blk{i}"]["relu2.in"] > 0]
+    return out
+
+
+def reconcile_relu_masks(om, dev_signs, blocks):
+    """The device's ReLU sign patterns as the mask list O.MLPResNet.backward takes, after checking
+    that they differ from the oracle's only where the oracle's pre-activation is within rounding
+    distance of zero.  Returns (masks, number of differing entries)."""
+    T = om.tape
+    pre = [T["lin0.pre"]]
+    for i in range(blocks):
+        pre += [T[f"blk{i}"]["relu1.in"], T[f"blk{i}"]["relu2.in"]]
+    flips = 0
+    for z, dev in zip(pre, dev_signs):
+        diff = dev != (z > 0)
+        n = int(diff.sum())
+        if n:
+            flips += n
+            # both sides computed the same sum of O(1) terms to ~1e-7 relative of the terms
+            assert float(np.abs(z[diff]).max()) <= 2e-6 * max(1.0, float(np.abs(z).max())), float(np.abs(z[diff]).max())
+    return [np.asarray(d, "float32") for d in dev_signs], flips

@@ -27,10 +27,10 @@ that reads them in this step (the layer's own forward and backward) was queued o
 compute stream before the event its bucket waits for.
 
 Rendezvous: ranks come from the environment torchrun sets (RANK, LOCAL_RANK,
-WORLD_SIZE, MASTER_ADDR, MASTER_PORT).  `torch.distributed` is used for exactly
-one thing -- a TCPStore to hand the 128-byte NCCL unique id from rank 0 to the
-others and for host-side barriers / gathers of a few floats; no tensor ever goes
-through it and it is not on the device path.
+WORLD_SIZE, MASTER_ADDR, MASTER_PORT).  The 128-byte NCCL unique id goes from rank 0 to the
+others through a file under /dev/shm (class Rendezvous), as do host-side barriers and the few
+floats the benchmark gathers; no tensor ever goes through it, it is not on the device path, and
+neither torch nor torch.distributed is imported by a training process.
 """
 from __future__ import annotations
 
@@ -66,37 +66,98 @@ def shard_rows(n_rows: int, rank: int, world: int) -> slice:
 
 
 class Rendezvous:
-    """Host-side key/value plumbing over torch.distributed.TCPStore."""
+    """Host-side key/value plumbing between the ranks of ONE node: small files under /dev/shm.
+
+    Nothing but the 128-byte NCCL id, barriers and a few floats for reporting ever goes through it
+    ("a /dev/shm file"); no tensor does, it is not on the device path, and the
+    process imports neither torch nor a socket library for it.  The directory is keyed by the
+    rendezvous port and the launcher's pid (all ranks of a torchrun job share their parent), rank 0
+    creates it afresh and removes it on `close()` / interpreter exit.  Values are written to a
+    temporary name and renamed, so a reader sees a whole value or none."""
 
     def __init__(self, env: Env, timeout_s: float = 300.0):
-        from datetime import timedelta
-        from torch.distributed import TCPStore
+        import atexit
+        import shutil
+        import tempfile
         self.env = env
+        self.timeout_s = float(timeout_s)
         self._n = 0
-        self.store = TCPStore(env.master_addr, env.master_port + 17, env.world, env.rank == 0,
-                              timeout=timedelta(seconds=timeout_s), wait_for_workers=True)
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        job = os.environ.get("SOKET_B200_RDV_ID") or f"{env.master_port}_{os.getppid()}"
+        self.dir = os.path.join(base, f"soket_b200_rdv_{job}")
+        self._closed = False
+        if env.rank == 0:
+            shutil.rmtree(self.dir, ignore_errors=True)       # a crashed earlier job with the same key
+            os.makedirs(self.dir + ".new", exist_ok=True)
+            os.rename(self.dir + ".new", self.dir)
+        else:
+            self._wait(lambda: os.path.isdir(self.dir), "the rendezvous directory of rank 0")
+        atexit.register(self.close)
+
+    def _wait(self, ready, what):
+        import time
+        t0 = time.monotonic()
+        pause = 0.0002
+        while not ready():
+            if time.monotonic() - t0 > self.timeout_s:
+                raise TimeoutError(f"soket_b200.dp rendezvous: rank {self.env.rank} waited {self.timeout_s:.0f} s for {what} "
+                                   f"in {self.dir}")
+            time.sleep(pause)
+            pause = min(pause * 1.5, 0.01)
+
+    def _put(self, key: str, payload: bytes):
+        path = os.path.join(self.dir, key)
+        tmp = f"{path}.tmp{self.env.rank}"
+        with open(tmp, "wb") as f:
+            f.write(payload)
+        os.rename(tmp, path)
+
+    def _get(self, key: str) -> bytes:
+        path = os.path.join(self.dir, key)
+        self._wait(lambda: os.path.exists(path), f"key {key!r}")
+        with open(path, "rb") as f:
+            return f.read()
 
     def broadcast_bytes(self, payload: bytes | None, key: str) -> bytes:
-        if self.env.rank == 0:
-            self.store.set(key, payload)
-            return payload
-        return bytes(self.store.get(key))
-
-    def barrier(self):
+        """Rank 0's `payload` on every rank.  Collective: the n-th call on every rank is one exchange."""
         self._n += 1
-        key = f"barrier/{self._n}"
-        self.store.add(key, 1)
-        import time
-        while int(self.store.add(key, 0)) < self.env.world:
-            time.sleep(0.0005)
+        name = f"bc_{self._n}_{key}"
+        if self.env.rank == 0:
+            self._put(name, payload)
+            return payload
+        return self._get(name)
+
+    def all_gather_bytes(self, payload: bytes) -> list[bytes]:
+        self._n += 1
+        self._put(f"ag_{self._n}_{self.env.rank}", payload)
+        return [self._get(f"ag_{self._n}_{r}") for r in range(self.env.world)]
 
     def all_gather_str(self, value: str) -> list[str]:
-        self._n += 1
-        self.store.set(f"ag/{self._n}/{self.env.rank}", value)
-        return [self.store.get(f"ag/{self._n}/{r}").decode() for r in range(self.env.world)]
+        return [b.decode() for b in self.all_gather_bytes(value.encode())]
+
+    def barrier(self):
+        self.all_gather_str("")
 
     def all_gather_float(self, value: float) -> list[float]:
         return [float(v) for v in self.all_gather_str(repr(float(value)))]
+
+    def close(self):
+        """Rank 0 removes the directory (call after a final barrier; also runs at interpreter exit)."""
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            self._put(f"done_{self.env.rank}", b"")
+        except OSError:
+            return
+        if self.env.rank == 0:
+            import shutil
+            import time
+            t0 = time.monotonic()       # the others may still be reading the last exchange
+            while (time.monotonic() - t0 < 10.0
+                   and not all(os.path.exists(os.path.join(self.dir, f"done_{r}")) for r in range(self.env.world))):
+                time.sleep(0.002)
+            shutil.rmtree(self.dir, ignore_errors=True)
 
 
 def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:

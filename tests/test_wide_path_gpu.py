@@ -24,6 +24,7 @@ import numpy as np
 import pytest
 
 from oracle import ref_model, soket_np as O
+from oracle.ref_model import device_relu_signs, oracle_relu_signs, reconcile_relu_masks
 
 pytestmark = pytest.mark.gpu
 
@@ -68,31 +69,6 @@ def make_pair(norm="layer", seed=0, hidden=HIDDEN, blocks=BLOCKS):
     return om, model, named
 
 
-def device_relu_signs(model, X, blocks):
-    """The sign pattern of every ReLU input of the FUSED forward (y > 0 <=> pre-activation > 0), read
-    off the fused kernels' own outputs through Sequential._run prefixes."""
-    import soket_b200.api as soket
-    signs = []
-    h = model._run(soket.Tensor(X), 2)                       # relu(lin0(X)): GEMM with bias+ReLU epilogue
-    signs.append(h.numpy() > 0)
-    mods = list(model._storage)
-    for i in range(blocks):
-        blk = mods[2 + i]
-        r1 = blk.fn._run(h, 3)                               # relu(LN1(lin1(h))): LN kernel, ReLU epilogue
-        signs.append(r1.numpy() > 0)
-        h = blk(h)                                           # relu(h + LN2(...)): LN kernel, residual epilogue
-        signs.append(h.numpy() > 0)
-    return signs
-
-
-def oracle_relu_signs(om, blocks):
-    T = om.tape
-    out = [T["lin0.pre"] > 0]
-    for i in range(blocks):
-        out += [T[f"blk{i}"]["relu1.in"] > 0, T[f"blk{i}"]["relu2.in"] > 0]
-    return out
-
-
 def sync_device_from_oracle(soket, sk, named, om, dev_opt, ora_opt, opt):
     for k, t in named.items():
         t.data = soket.Tensor(om.params[k].copy())
@@ -103,25 +79,6 @@ def sync_device_from_oracle(soket, sk, named, om, dev_opt, ora_opt, opt):
             shp = om.params[k].shape
             dev_opt._u[i] = None if ora_opt.u[j] is None else sk.array(np.ascontiguousarray(ora_opt.u[j], dtype="float32").reshape(shp))
             dev_opt._v[i] = None if ora_opt.v[j] is None else sk.array(np.ascontiguousarray(ora_opt.v[j], dtype="float32").reshape(shp))
-
-
-def reconcile_relu_masks(om, dev_signs, blocks):
-    """The device's ReLU sign patterns as the mask list O.MLPResNet.backward takes, after checking
-    that they differ from the oracle's only where the oracle's pre-activation is within rounding
-    distance of zero.  Returns (masks, number of differing entries)."""
-    T = om.tape
-    pre = [T["lin0.pre"]]
-    for i in range(blocks):
-        pre += [T[f"blk{i}"]["relu1.in"], T[f"blk{i}"]["relu2.in"]]
-    flips = 0
-    for z, dev in zip(pre, dev_signs):
-        diff = dev != (z > 0)
-        n = int(diff.sum())
-        if n:
-            flips += n
-            # both sides computed the same sum of O(1) terms to ~1e-7 relative of the terms
-            assert float(np.abs(z[diff]).max()) <= 2e-6 * max(1.0, float(np.abs(z).max())), float(np.abs(z[diff]).max())
-    return [np.asarray(d, "float32") for d in dev_signs], flips
 
 
 @pytest.mark.parametrize("opt", ["sgd", "adam"])
