@@ -464,16 +464,18 @@ def run_ours(args, env):
     marks = [sk.Event() for _ in range(args.steps)]
     ev0.record()
     last = None
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         last = step_resident()
         marks[i].record()
+    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # host time to ISSUE a step (no sync inside)
     ev1.record()
     ev1.synchronize()
     barrier()
     ms = ev0.elapsed_ms(ev1)
     per_step = [(ev0 if i == 0 else marks[i - 1]).elapsed_ms(marks[i]) for i in range(args.steps)]
-    print(f"[bench rank {env.rank}] per-step ms (timed region): " + " ".join(f"{t:.2f}" for t in per_step),
-          file=sys.stderr, flush=True)
+    print(f"[bench rank {env.rank}] per-step ms (timed region): " + " ".join(f"{t:.2f}" for t in per_step)
+          + f" | host issue {host_issue_ms:.2f} ms/step", file=sys.stderr, flush=True)
     launches = sk.launch_count() - launches0
     loss_value = last.item()
 
@@ -517,6 +519,7 @@ def run_ours(args, env):
     if rdv is not None:
         acc = {"forward": 0.0, "backward": 0.0, "comm_after_backward": 0.0, "optimizer_after_comm": 0.0, "step": 0.0}
         evs = [sk.Event() for _ in range(3)]
+        bucket_acc = []          # per bucket: MB, gradients complete / all-reduce done, ms after backward started
         barrier()
         for _ in range(args.steps):
             evs[0].record()
@@ -533,7 +536,13 @@ def run_ours(args, env):
             acc["comm_after_backward"] += tail
             acc["optimizer_after_comm"] += max(evs[2].elapsed_ms(ev_done) - tail, 0.0)
             acc["step"] += evs[0].elapsed_ms(ev_done)
+            for j, (mb, ready, reduced) in enumerate(ddp.bucket_times(evs[1])):
+                if j == len(bucket_acc):
+                    bucket_acc.append([mb, 0.0, 0.0])
+                bucket_acc[j][1] += ready / args.steps
+                bucket_acc[j][2] += reduced / args.steps
         dp_timeline = {k: v / args.steps for k, v in acc.items()}
+        dp_timeline["buckets"] = [{"mb": round(mb, 2), "ready_ms": round(a, 3), "reduced_ms": round(b, 3)} for mb, a, b in bucket_acc]
         dp_timeline["note"] = ("ms per step on this rank, CUDA events: forward / backward on the compute stream; "
                                "comm_after_backward = the last bucket's all-reduce finishing after backward's last "
                                "kernel (exposed communication); optimizer_after_comm = the last buckets' Adam + weight "
@@ -579,7 +588,7 @@ def run_ours(args, env):
             "config": workload_config(args, env.world, batch),
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": int(Xh.nbytes + yh.nbytes), "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms,
             "clocks": clock_info,
             "roofline": {
                 "bound": "tensor", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

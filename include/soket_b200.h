@@ -466,6 +466,47 @@ int sk_nccl_allreduce_on(float *buf, size_t count, int stream_id);
 int sk_nccl_abort(void);
 int sk_nccl_destroy(void);
 
+/* ---- data parallel over NVLink peer memory (no collective library on the data path) ----------------
+ * new ("the gradient all-reduce is the only exchange step"; the reference has no
+ * multi-GPU code to replace).  One kernel per gradient bucket does reduce-scatter + Adam on this rank's
+ * shard + the GEMM weights' fp16x3 operand split + all-gather of the new weights, reading the peers'
+ * gradient arenas and writing every replica's parameter / split arenas directly (csrc/dp_p2p.cu).
+ * The arenas (one cudaMalloc block each, same layout on every rank) are exchanged as CUDA IPC handles. */
+#define SK_IPC_HANDLE_BYTES 64
+#define SK_P2P_MAX_WORLD 8
+#define SK_P2P_MAX_BUCKETS 256
+int sk_ipc_export(const void *ptr, char handle[SK_IPC_HANDLE_BYTES], int64_t *offset);
+int sk_ipc_open(const char handle[SK_IPC_HANDLE_BYTES], int64_t offset, void **ptr);
+int sk_ipc_close_all(void);
+typedef struct {
+    int world, rank, n_buckets, n_slots;
+    float *grads[SK_P2P_MAX_WORLD];          /* fp32 gradient arenas, [rank] = this process's own */
+    float *params[SK_P2P_MAX_WORLD];         /* fp32 parameter arenas */
+    void *hi[SK_P2P_MAX_WORLD];              /* fp16 operand-split arenas (element offsets as in params), or NULL */
+    void *lo[SK_P2P_MAX_WORLD];
+    /* uint32 words: ready[n_buckets][8], done[n_buckets][8], parts[2][n_slots][8] (zero at start, except
+     * parts[1][slot][*] = bit pattern of max |w| of every GEMM weight before the first step) */
+    unsigned int *flags[SK_P2P_MAX_WORLD];
+} sk_p2p_peers;
+typedef struct {
+    int64_t offset;          /* element offset of the tensor in the arenas */
+    int64_t start, count;    /* this rank's shard of it (count may be 0) */
+    float *m, *v;            /* Adam moments of the shard (local, count elements) */
+    float *scale4;           /* float[4] of the weight's operand split on THIS rank, or NULL (no split) */
+    int slot;                /* row of the parts table (one per tensor) */
+    int first;               /* first update of this tensor (optim.pyx:224-238) */
+} sk_p2p_tensor;
+typedef struct {
+    double lr, beta1, beta2, eps, weight_decay, one_minus_beta1_t, one_minus_beta2_t, grad_scale, update_bound;
+    int share_grads;         /* also leave the reduced gradient (sum over ranks) in every replica's arena */
+} sk_p2p_adam;
+/* on the current launch stream (sk_launch_stream), after the bucket's last gradient kernel in stream order;
+ * scratch = SK_P2P_MAX_BUCKETS + n_slots zeroed device words owned by the caller */
+int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int n_tensors,
+                     const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper, unsigned int *scratch);
+/* the current launch stream waits until every peer has finished `step` on the buckets in the mask */
+int sk_dp_p2p_wait(const unsigned int *flags, int n_buckets, int world, unsigned int step, const unsigned int *bucket_mask);
+
 #ifdef __cplusplus
 }
 #endif

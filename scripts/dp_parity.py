@@ -48,7 +48,12 @@ def main():
         w = om.params[k] if env.rank == 0 else np.full_like(om.params[k], 7.0)
         t.data = soket.Tensor(w.copy())
     opt = Adam(model.parameters(), lr=1e-3) if use_adam else SGD(model.parameters(), lr=0.05)
-    ddp = dp.DataParallel(opt, rdv, bucket_mb=float(os.environ.get("DP_BUCKET_MB", "0.25")))   # several buckets
+    # DP_MODE=p2p: reduce-scatter + Adam + operand split + all-gather as one kernel per bucket over NVLink peer
+    # memory instead of ncclAllReduce + replicated Adam; share_grads leaves the reduced gradient in every
+    # replica's arena so that the gradient check below reads the same thing in both modes
+    mode = os.environ.get("DP_MODE", "nccl")
+    ddp = dp.DataParallel(opt, rdv, bucket_mb=float(os.environ.get("DP_BUCKET_MB", "0.25")), mode=mode,
+                          share_grads=True)   # several buckets
     ddp.broadcast_parameters(0)
     crit = nn.SoftmaxCrossEntropyLoss()
     oo = O.Adam(len(om.names()), lr=1e-3) if use_adam else O.SGD(len(om.names()), lr=0.05)
@@ -142,7 +147,7 @@ def main():
             per.append((e, k))
             worst = max(worst, e)
         print("worst tensors:", sorted(per, reverse=True)[:4], flush=True)
-        print(f"dp parity W={env.world} norm={norm} opt={'adam' if use_adam else 'sgd'}: "
+        print(f"dp parity W={env.world} mode={mode} norm={norm} opt={'adam' if use_adam else 'sgd'}: "
               f"worst update rel err {worst:.2e} over {steps} step(s), {total_flips} reconciled ReLU sign(s)", flush=True)
         # a plumbing bug (a tensor not all-reduced, a missing 1/W, a wrong shard) shows up as an O(1)
         # update error; with the ReLU sign patterns reconciled both sides stay at rounding distance
@@ -150,10 +155,66 @@ def main():
         assert worst <= 2e-4, worst
     rdv.barrier()
     ddp.close()
-    if use_adam and wide:
+    if use_adam and wide and mode == "nccl":
         fused_split_check(env, rdv, start, dim, hidden, nb, C, B)
+    if use_adam and mode == "p2p":
+        p2p_matches_nccl_check(env, rdv, start, dim, hidden, nb, C, B)
     rdv.barrier()
     rdv.close()
+
+
+def p2p_matches_nccl_check(env, rdv, start, dim, hidden, nb, C, B):
+    """Six free-running Adam steps in both data-parallel modes from the same start.  The two modes do the same
+    arithmetic per element (sum of the ranks' gradients, then the optimizer's update, csrc/optim.cuh) and differ
+    in the ORDER of the W-term gradient sum only: at W = 2 (one commutative add) the parameters must be
+    bit-identical on every rank, beyond that they agree to rounding.  Also checks that the replicas stay
+    replicas and that only 1/W of the optimizer state lives on each rank."""
+    runs = {}
+    for mode in ("p2p", "nccl"):
+        model = ref_model.build_model(nn, dim, hidden, nb, C, norm="layer", drop_prob=0.0)
+        named = ref_model.named_parameters(model, nb)
+        for k, t in named.items():
+            t.data = soket.Tensor((start[k] if env.rank == 0 else np.full_like(start[k], 3.0)).copy())
+        opt = Adam(model.parameters(), lr=1e-3)
+        ddp = dp.DataParallel(opt, rdv, bucket_mb=0.25, mode=mode)
+        ddp.broadcast_parameters(0)
+        crit = nn.SoftmaxCrossEntropyLoss()
+        rng = np.random.default_rng(11)
+        sl = dp.shard_rows(B, env.rank, env.world)
+        losses = []
+        for step in range(6):
+            X = rng.random((B, dim), dtype=np.float32)
+            y = rng.integers(0, C, B).astype(np.uint8)
+            loss = crit(model(soket.Tensor(X[sl])), soket.Tensor(y[sl]))
+            loss.backward()
+            ddp.step()
+            losses.append(loss.item())
+        params = {k: t.numpy() for k, t in named.items()}
+        digest = repr(float(sum(float(np.abs(v.astype(np.float64)).sum()) for v in params.values())))
+        assert len(set(rdv.all_gather_str(digest))) == 1, "replicas diverged in mode " + mode
+        if mode == "p2p":
+            state = sum(int(m.size) for m in ddp._m if m is not None)
+            total = sum(int(t.size) for t in named.values())
+            assert state <= total // env.world + 4096, (state, total)
+        runs[mode] = (params, losses)
+        rdv.barrier()
+        ddp.close()
+    (pp, lp), (pn, ln) = runs["p2p"], runs["nccl"]
+    worst = 0.0
+    for k in pp:
+        if env.world == 2:
+            assert np.array_equal(pp[k], pn[k]), (k, float(np.abs(pp[k] - pn[k]).max()))
+        else:
+            upd = max(float(np.abs(pn[k] - start[k]).max()), 1e-30)
+            worst = max(worst, float(np.abs(pp[k] - pn[k]).max()) / upd)
+    if env.world == 2:
+        assert lp == ln, (lp, ln)
+    else:
+        assert worst <= 2e-2, worst         # Adam's lr * sign(g) on elements whose gradient is rounding residue
+        assert max(abs(a - b) for a, b in zip(lp, ln)) <= 1e-4, (lp, ln)
+    if env.rank == 0:
+        print(f"dp p2p vs nccl W={env.world}: 6 Adam steps " + ("bit-identical parameters and losses" if env.world == 2
+              else f"worst update difference {worst:.2e}") + f" (losses {lp[0]:.6f} -> {lp[-1]:.6f})", flush=True)
 
 
 def fused_split_check(env, rdv, start, dim, hidden, nb, C, B):

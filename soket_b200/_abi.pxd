@@ -265,3 +265,40 @@ cdef extern from "soket_b200.h" nogil:
     int sk_nccl_destroy()
     int sk_nccl_allreduce_on(float *buf, size_t count, int stream_id)
     int sk_nccl_abort()
+
+    int sk_ipc_export(const void *ptr, char *handle, int64_t *offset)
+    int sk_ipc_open(const char *handle, int64_t offset, void **ptr)
+    int sk_ipc_close_all()
+    ctypedef struct sk_p2p_peers:
+        int world
+        int rank
+        int n_buckets
+        int n_slots
+        float *grads[8]
+        float *params[8]
+        void *hi[8]
+        void *lo[8]
+        unsigned int *flags[8]
+    ctypedef struct sk_p2p_tensor:
+        int64_t offset
+        int64_t start
+        int64_t count
+        float *m
+        float *v
+        float *scale4
+        int slot
+        int first
+    ctypedef struct sk_p2p_adam:
+        double lr
+        double beta1
+        double beta2
+        double eps
+        double weight_decay
+        double one_minus_beta1_t
+        double one_minus_beta2_t
+        double grad_scale
+        double update_bound
+        int share_grads
+    int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int n_tensors,
+                         const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper, unsigned int *scratch)
+    int sk_dp_p2p_wait(const unsigned int *flags, int n_buckets, int world, unsigned int step, const unsigned int *bucket_mask)

@@ -7,6 +7,7 @@ cdef class Buffer:
     cdef size_t ptr
     cdef size_t nbytes
     cdef long version           # bumped by every in-place write through any view (see ndarray._touch)
+    cdef object parent          # set for a window into another Buffer's allocation (arena_view): not freed here
 
 
 cdef class ndarray:

@@ -97,11 +97,12 @@ cdef class Buffer:
         self.ptr = 0
         self.nbytes = 0
         self.version = 0
+        self.parent = None
 
     def __dealloc__(self):
-        if self.ptr != 0:
+        if self.ptr != 0 and self.parent is None:
             sk_free(<void *> self.ptr)
-            self.ptr = 0
+        self.ptr = 0
 
 
 cdef Buffer _alloc(size_t nbytes):
@@ -111,6 +112,37 @@ cdef Buffer _alloc(size_t nbytes):
     b.ptr = <size_t> p
     b.nbytes = nbytes
     return b
+
+
+def arena_view(ndarray arena, int64_t offset, shape):
+    """A C-contiguous array of `shape` over elements [offset, offset + prod(shape)) of the 1-D contiguous
+    `arena`, with a write-version of its OWN (data-parallel training keeps every parameter in one
+    IPC-exported allocation; an in-place update of one parameter must not invalidate the operand
+    splits derived from the others).  The window keeps the arena's allocation alive."""
+    cdef ndarray a = ndarray.__new__(ndarray)
+    cdef int64_t n = 1
+    cdef int i, ndim = len(shape)
+    if arena._ndim != 1 or not arena._is_contiguous():
+        raise ValueError('arena_view: the arena must be a contiguous 1-D array')
+    if ndim > SK_MAX_NDIM:
+        raise ValueError(f'soket_b200: at most {SK_MAX_NDIM} dimensions are supported')
+    a._ndim = ndim
+    for i in range(ndim - 1, -1, -1):
+        a._shape[i] = shape[i]
+        a._strides[i] = n
+        n *= shape[i]
+    if offset < 0 or offset + n > arena._shape[0]:
+        raise ValueError('arena_view: window outside the arena')
+    a._code = arena._code
+    a._np_dtype = arena._np_dtype
+    cdef Buffer b = Buffer.__new__(Buffer)
+    b.ptr = arena._ptr + <size_t> (offset * _ITEMSIZE[arena._code])
+    b.nbytes = <size_t> n * _ITEMSIZE[arena._code]
+    b.parent = arena._buf
+    a._buf = b
+    a._ptr = b.ptr
+    a._readonly = False
+    return a
 
 
 cdef ndarray _new_array(int ndim, const int64_t *shape, int code):
@@ -1471,17 +1503,32 @@ def bind_absmax(AbsMax a, ndarray x):
     x._meta = a
 
 
-def split_f16(x, want_colsum=False, out_colsum=None):
+def split_f16(x, want_colsum=False, out_colsum=None, out_hi=None, out_lo=None):
     """float32 (rows, cols) -> SplitMat (and the column sums of x when asked: the bias gradient rides
     along with the adjoint's split, autodiff.pyx:84).  Uses the |max| a producing kernel attached to
-    x (AbsMax) when there is one, else computes it in an extra pass."""
+    x (AbsMax) when there is one, else computes it in an extra pass.  out_hi / out_lo: caller-owned
+    contiguous float16 (rows, cols) arrays to split into (cols % 8 == 0)."""
     cdef ndarray a = _as_device(x)
     if a._ndim != 2 or a._code != SK_F32:
         raise TypeError('split_f16: expected a 2-D float32 array')
     a = a._compact()
     if a._shape[1] % 4 != 0 and a._shape[0] > 1:
         raise ValueError('split_f16: the row length must be a multiple of 4 elements (16-byte aligned rows)')
-    cdef SplitMat m = _new_split(a._shape[0], a._shape[1])
+    cdef SplitMat m
+    cdef int64_t four = 4
+    if out_hi is not None:
+        m = SplitMat.__new__(SplitMat)
+        m.rows = a._shape[0]; m.cols = a._shape[1]; m.ld = m.cols
+        m.hi = <ndarray> out_hi; m.lo = <ndarray> out_lo
+        for h in (m.hi, m.lo):
+            if ((<ndarray> h)._code != SK_F16 or (<ndarray> h)._numel() != m.rows * m.cols or not (<ndarray> h)._is_contiguous()
+                    or m.cols % 8 != 0):
+                raise ValueError('split_f16: out_hi / out_lo must be contiguous float16 arrays of x\'s size (cols % 8 == 0)')
+        m.scale = _new_array(1, &four, SK_F32)
+        m.src_ptr = 0; m.version = -1; m.epoch = -1; m.capture = 0
+        m.amax = None
+    else:
+        m = _new_split(a._shape[0], a._shape[1])
     cdef const unsigned int *amax = NULL
     cdef AbsMax am = None
     if isinstance(a._meta, AbsMax):
@@ -1510,6 +1557,11 @@ def split_f16(x, want_colsum=False, out_colsum=None):
     if want_colsum:
         return m, cs
     return m
+
+
+def rebind_split(SplitMat m, ndarray x):
+    """m's hi / lo were rewritten (by a kernel the caller launched) to describe x's CURRENT contents."""
+    _bind_split(m, x)
 
 
 def get_split(x):

@@ -443,3 +443,98 @@ def nccl_wait():
 
 def nccl_destroy():
     _check(sk_nccl_destroy())
+
+
+# ---------------------------------------------------------------- data parallel over peer memory
+def ipc_export(ndarray a):
+    """(64-byte CUDA IPC handle of the allocation `a` lives in, byte offset of a's first element in it)."""
+    cdef char h[64]
+    cdef int64_t off = 0
+    _check(sk_ipc_export(<const void *> a._ptr, h, &off))
+    return bytes(h[:64]), int(off)
+
+
+def ipc_open(bytes handle, int64_t offset):
+    """Map a peer's allocation into this process; returns the device address of its exported array."""
+    if len(handle) != 64:
+        raise ValueError('ipc_open: the handle must be 64 bytes')
+    cdef void *p = NULL
+    _check(sk_ipc_open(<const char *> handle, offset, &p))
+    return <size_t> p
+
+
+def ipc_close_all():
+    _check(sk_ipc_close_all())
+
+
+cdef class P2pPeers:
+    """The arenas of every rank as this process sees them (soket_b200.dp, mode 'p2p')."""
+    cdef sk_p2p_peers c
+    cdef public ndarray scratch
+    cdef public ndarray flags
+    cdef public int n_buckets
+
+    def __init__(self, int world, int rank, int n_buckets, int n_slots, list grads, list params, list hi, list lo,
+                 list flags, ndarray own_flags):
+        cdef int q
+        if world < 2 or world > 8 or len(grads) != world or len(params) != world or len(flags) != world:
+            raise ValueError('P2pPeers: 2..8 ranks, one address per rank and arena')
+        self.c.world = world; self.c.rank = rank; self.c.n_buckets = n_buckets; self.c.n_slots = n_slots
+        for q in range(8):
+            self.c.grads[q] = NULL; self.c.params[q] = NULL; self.c.hi[q] = NULL; self.c.lo[q] = NULL; self.c.flags[q] = NULL
+        for q in range(world):
+            self.c.grads[q] = <float *> <size_t> grads[q]
+            self.c.params[q] = <float *> <size_t> params[q]
+            self.c.hi[q] = <void *> <size_t> hi[q]
+            self.c.lo[q] = <void *> <size_t> lo[q]
+            self.c.flags[q] = <unsigned int *> <size_t> flags[q]
+        self.flags = own_flags
+        self.n_buckets = n_buckets
+        self.scratch = _B.zeros((256 + max(n_slots, 1),), 'uint32')
+
+
+def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, list tensors, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
+                  double grad_scale, double update_bound, bint share_grads):
+    """One bucket of the peer-memory data-parallel Adam step (sk_dp_p2p_update) on the current launch stream.
+    tensors: [(param ndarray, arena offset, shard start, shard count, m, v, SplitMat or None, slot, first)]."""
+    cdef int n = len(tensors), i
+    cdef sk_p2p_tensor *ts = <sk_p2p_tensor *> malloc(max(n, 1) * sizeof(sk_p2p_tensor))
+    if ts == NULL:
+        raise MemoryError()
+    cdef sk_p2p_adam h
+    cdef ndarray p
+    cdef SplitMat sm
+    h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay
+    h.one_minus_beta1_t = one_minus_beta1_t; h.one_minus_beta2_t = one_minus_beta2_t
+    h.grad_scale = grad_scale; h.update_bound = update_bound; h.share_grads = 1 if share_grads else 0
+    try:
+        for i in range(n):
+            p, off, start, count, m, v, split, slot, first = tensors[i]
+            ts[i].offset = off; ts[i].start = start; ts[i].count = count
+            ts[i].m = _fptr(<ndarray> m) if count else NULL
+            ts[i].v = _fptr(<ndarray> v) if count else NULL
+            ts[i].scale4 = NULL
+            if split is not None:
+                sm = <SplitMat> split
+                ts[i].scale4 = <float *> sm.scale._ptr
+            ts[i].slot = slot; ts[i].first = 1 if first else 0
+        _check(sk_dp_p2p_update(&peers.c, bucket, step, n, ts, &h, <unsigned int *> peers.scratch._ptr))
+    finally:
+        free(ts)
+    for i in range(n):
+        p = <ndarray> tensors[i][0]
+        p._touch()                                       # every replica of p is rewritten by this launch
+        if tensors[i][6] is not None:
+            _bind_split(<SplitMat> tensors[i][6], p)     # ... and so is its operand split
+
+
+def dp_p2p_wait(P2pPeers peers, unsigned int step, list bucket_ids):
+    """The current launch stream waits until every rank has finished `step` on these buckets."""
+    cdef unsigned int mask[8]
+    cdef int i
+    for i in range(8):
+        mask[i] = 0
+    for b in bucket_ids:
+        mask[b >> 5] |= (<unsigned int> 1) << (b & 31)
+    _check(sk_dp_p2p_wait(<const unsigned int *> peers.flags._ptr, peers.n_buckets, peers.c.world, step, mask))

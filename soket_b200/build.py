@@ -35,7 +35,7 @@ NVCC_FLAGS = [
 
 CU_SOURCES = [
     "runtime.cu", "ewise.cu", "reduce.cu", "index.cu", "rng.cu",
-    "matmul.cu", "matmul_simt.cu", "matmul_tc.cu", "matmul_tc2.cu", "matmul_split.cu", "nn_fused.cu", "optim.cu", "dp.cu",
+    "matmul.cu", "matmul_simt.cu", "matmul_tc.cu", "matmul_tc2.cu", "matmul_split.cu", "nn_fused.cu", "optim.cu", "dp.cu", "dp_p2p.cu",
 ]
 
 

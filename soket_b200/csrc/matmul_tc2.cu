@@ -457,7 +457,11 @@ static int launch_kind2(const GemmProblem &g, const Operand &oa, const Operand &
   }
   p.sched = dyn_env ? sched_dev : nullptr;
   const int tiles = p.tiles_m * p.tiles_n;
-  const int max_pairs = ctx().num_sms / 2;
+  // SOKET_B200_GEMM_RESERVE_SMS: SMs the persistent grid leaves alone (data-parallel training: the collective's
+  // CTAs then never queue behind a GEMM CTA that holds its SM for a whole tile)
+  static const int reserve_env = getenv("SOKET_B200_GEMM_RESERVE_SMS") ? atoi(getenv("SOKET_B200_GEMM_RESERVE_SMS")) : 0;
+  int max_pairs = (ctx().num_sms - reserve_env) / 2;
+  if (max_pairs < 1) max_pairs = 1;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
 #define LAUNCH2(AMN, BMN)                                                                                  \
   do {                                                                                                     \

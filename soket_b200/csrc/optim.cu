@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "matmul_split.cuh"
+#include "optim.cuh"
 
 namespace sk {
 
@@ -101,25 +102,6 @@ __global__ void __launch_bounds__(kOT) sgd_kernel(const __grid_constant__ SgdArg
   } else {
     for (int64_t i = base + threadIdx.x; i < n && i < base + kChunk; i += kOT) p[i] = sgd_one(p[i], g[i], a);
   }
-}
-
-__device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamArgs &a,
-                                         const float bc1, const float bc2) {
-  if (a.have_scale) g = __fmul_rn(g, a.grad_scale);
-  if (a.have_wd) g = __fadd_rn(g, __fmul_rn(p, a.wd));  // optim.pyx:220-222
-  const float gm = __fmul_rn(g, a.omb1);                 // grad * (1 - beta1)
-  const float gv = __fmul_rn(g, __fmul_rn(g, a.omb2));   // grad * (grad * (1 - beta2))
-  if (a.first) {  // optim.pyx:224-238: first step has no beta*state term
-    m = gm;
-    v = gv;
-  } else {
-    m = __fadd_rn(__fmul_rn(m, a.beta1), gm);
-    v = __fadd_rn(__fmul_rn(v, a.beta2), gv);
-  }
-  const float mh = __fdiv_rn(m, bc1);  // optim.pyx:246-247
-  const float vh = __fdiv_rn(v, bc2);
-  // p - lr * (mh / (pow(vh, 0.5) + eps))   optim.pyx:254-263 ; quirk Q3: maximize is a no-op
-  p = __fsub_rn(p, __fmul_rn(a.lr, __fdiv_rn(mh, __fadd_rn(__fsqrt_rn(vh), a.eps))));
 }
 
 __global__ void __launch_bounds__(kOT) adam_kernel(const __grid_constant__ AdamArgs a) {

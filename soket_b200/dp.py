@@ -160,6 +160,16 @@ class Rendezvous:
             shutil.rmtree(self.dir, ignore_errors=True)
 
 
+def shard_of(n: int, index: int, rank: int, world: int):
+    """(start, count) of rank's shard of parameter number `index` with n elements under the peer-memory
+    update: `world` equal shards when n splits into whole 16-byte vectors per rank, else the whole tensor
+    on ONE owner rank (index % world) and nothing on the others.  Pure host logic (CPU-tested)."""
+    if n % (4 * world) == 0:
+        c = n // world
+        return rank * c, c
+    return (0, n) if rank == index % world else (0, 0)
+
+
 def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:
     """Rank 0 creates the NCCL unique id; every rank returns the same 128 bytes."""
     uid = make_id() if rdv.env.rank == 0 else None
@@ -169,12 +179,13 @@ def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:
 SLOT_ALIGN = 64           # floats: every slot starts on a 256-byte boundary (vector loads, TMA-free GEMM epilogue)
 
 
-def plan_arena(sizes, bucket_floats):
+def plan_arena(sizes, bucket_floats, max_members=None):
     """Layout of the flat gradient arena for parameters of `sizes` elements (in parameter-list
     order).  Slots are placed in REVERSE order -- backward reaches the last layer first -- each
     aligned to SLOT_ALIGN floats, and cut greedily into buckets of at least `bucket_floats` floats.
     Returns (offsets, total, buckets) with offsets[i] the slot of parameter i and
-    buckets = [(start, end, [parameter indices in slot order])].  Pure host logic (CPU-tested)."""
+    buckets = [(start, end, [parameter indices in slot order])]; a bucket also closes at `max_members`
+    tensors (the peer-memory update kernel takes 32 per launch).  Pure host logic (CPU-tested)."""
     offsets = [0] * len(sizes)
     buckets = []
     off, start, members = 0, 0, []
@@ -182,7 +193,7 @@ def plan_arena(sizes, bucket_floats):
         offsets[i] = off
         off += (int(sizes[i]) + SLOT_ALIGN - 1) // SLOT_ALIGN * SLOT_ALIGN
         members.append(i)
-        if off - start >= bucket_floats:
+        if off - start >= bucket_floats or (max_members is not None and len(members) >= max_members):
             buckets.append((start, off, members))
             start, members = off, []
     if members:
@@ -200,6 +211,8 @@ class _Bucket:
     ev_reduced: object = None
     arrived: int = 0
     launched: bool = False
+    t_launch: int = -1
+    index: int = -1
     seen: set = field(default_factory=set)
 
 
@@ -216,14 +229,20 @@ class DataParallel:
     next backward, and after `step()` it holds the SUM over ranks (the 1/W is applied inside the
     optimizer kernel)."""
 
-    def __init__(self, optim, rdv: Rendezvous | None, overlap: bool = True, bucket_mb: float | None = None):
+    def __init__(self, optim, rdv: Rendezvous | None, overlap: bool = True, bucket_mb: float | None = None,
+                 mode: str | None = None, share_grads: bool | None = None):
         from soket_b200 import _core as B
         from soket_b200 import _fused as F
         from soket_b200 import engine as E
         self.B, self.F, self.E = B, F, E
         self.optim = optim
         self.world = 1 if rdv is None else rdv.env.world
+        self.rdv = rdv
+        self.mode = "nccl"
         self.overlap = overlap
+        # SOKET_B200_DP_OPT_OVERLAP=0: one optimizer launch after the last all-reduce instead of one per bucket
+        # beside backward (the HBM-bound update then does not compete with the GEMMs for bandwidth)
+        self.opt_overlap = os.environ.get("SOKET_B200_DP_OPT_OVERLAP", "1") != "0"
         self._closed = False
         if self.world == 1:
             return
@@ -239,7 +258,20 @@ class DataParallel:
         uid = exchange_unique_id(rdv, F.nccl_unique_id)
         F.nccl_init(rdv.env.rank, rdv.env.world, uid)
         optim.grad_scale = 1.0 / self.world
-        offsets, total, buckets = plan_arena([int(p.size) for p in params], int(bucket_mb * (1 << 20) / 4))
+        mode = mode or os.environ.get("SOKET_B200_DP_MODE", "nccl")
+        if mode not in ("nccl", "p2p"):
+            raise ValueError(f"DataParallel: unknown mode {mode!r} (nccl | p2p)")
+        if mode == "p2p":
+            why = self._p2p_unsupported()
+            if why:
+                raise ValueError(f"DataParallel(mode='p2p'): {why}")
+        self.mode = mode
+        if share_grads is None:
+            share_grads = os.environ.get("SOKET_B200_DP_SHARE_GRADS", "0") == "1"
+        self.share_grads = bool(share_grads)
+        offsets, total, buckets = plan_arena([int(p.size) for p in params], int(bucket_mb * (1 << 20) / 4),
+                                             max_members=32 if mode == "p2p" else None)
+        self._offsets, self._total = offsets, total
         self.arena = B.zeros((max(total, 1),), "float32")      # padding between slots stays zero
         self._slots = []
         for p, off in zip(params, offsets):
@@ -250,11 +282,15 @@ class DataParallel:
         self._where = {}
         for start, end, members in buckets:
             b = _Bucket(start, end, members, self.arena[start:end], B.Event(), B.Event())
+            b.index = len(self._buckets)
             for i in members:
                 self._where[id(params[i])] = (len(self._buckets), i)
             self._buckets.append(b)
         self._ev_done = B.Event()
         self._last_bucket = None
+        self._n_launch = 0
+        if mode == "p2p":
+            self._p2p_setup()
         E.set_leaf_grad_hook(self._on_leaf_grad)
 
     # ------------------------------------------------------------------------------------------
@@ -283,17 +319,149 @@ class DataParallel:
         if self.overlap and not b.launched and b.arrived == len(b.members):
             self._launch(b)
 
+    # ------------------------------------------------------------------------------------------
+    # mode 'p2p': reduce-scatter + Adam + operand split + all-gather as one kernel per bucket over NVLink peer
+    # memory (csrc/dp_p2p.cu).  The parameters move into ONE arena per rank (same layout as the gradient
+    # arena) that the peers map through CUDA IPC, the GEMM weights' fp16 hi / lo splits into two more; every
+    # rank keeps the Adam moments of its shard of every tensor only.
+    def _p2p_unsupported(self):
+        from soket_b200.optim import Adam, adam_ratio_bound
+        o = self.optim
+        if not isinstance(o, Adam):
+            return "the fused peer-memory update implements Adam (use mode='nccl' for other optimizers)"
+        if o._capturable:
+            return "Adam(capturable=True) is not supported"
+        if self.world > 8:
+            return "at most 8 ranks (one NVSwitch domain)"
+        if adam_ratio_bound(o._beta1, o._beta2, 1) is None:
+            return "no finite bound of |m_hat / sqrt(v_hat)| for these betas"
+        if any(u is not None for u in o._u):
+            return "the optimizer has already taken steps (its state is replicated)"
+        return None
+
+    def _p2p_setup(self):
+        import pickle
+        import numpy as np
+        B, F, E = self.B, self.F, self.E
+        params, rdv = self.optim._params, self.rdv
+        rank, world = rdv.env.rank, self.world
+        if len(self._buckets) > 256:
+            raise ValueError(f"DataParallel(mode='p2p'): {len(self._buckets)} buckets (at most 256): raise bucket_mb")
+        total = max(self._total, 1)
+        self._parena = B.zeros((total,), "float32")
+        self._hi = B.zeros((total,), "float16")
+        self._lo = B.zeros((total,), "float16")
+        nb, ns = len(self._buckets), len(params)
+        self._flag_words = 2 * nb * 8 + 2 * ns * 8
+        self._flags = B.zeros((self._flag_words,), "uint32")
+        self._split = [None] * ns
+        self._m, self._v, self._shard, self._fresh = [None] * ns, [None] * ns, [None] * ns, [True] * ns
+        for i, (p, off) in enumerate(zip(params, self._offsets)):
+            view = B.arena_view(self._parena, off, tuple(p.shape))
+            view[...] = p._data
+            p._data = view                                      # the tensor's storage IS its window of the arena
+            start, count = shard_of(int(p.size), i, rank, world)
+            self._shard[i] = (start, count)
+            if count:
+                self._m[i] = B.zeros((count,), "float32")
+                self._v[i] = B.zeros((count,), "float32")
+        B.synchronize()
+        mine = [F.ipc_export(a) for a in (self.arena, self._parena, self._hi, self._lo, self._flags)]
+        everyone = [pickle.loads(x) for x in rdv.all_gather_bytes(pickle.dumps(mine))]
+        own = [a.data_ptr for a in (self.arena, self._parena, self._hi, self._lo, self._flags)]
+        addr = [[own[k] if q == rank else F.ipc_open(*everyone[q][k]) for q in range(world)] for k in range(5)]
+        self._peers = F.P2pPeers(world, rank, nb, ns, addr[0], addr[1], addr[2], addr[3], addr[4], self._flags)
+        self._p2p_ready = False
+        self._step = 1
+        rdv.barrier()                                           # every rank has mapped every arena
+
+    def _p2p_prepare(self):
+        """Before the first update (and after `broadcast_parameters`): every GEMM weight's operand split moves
+        into the hi / lo arenas and its |max| seeds the table the kernels derive the split scale from."""
+        import numpy as np
+        B, E = self.B, self.E
+        params = self.optim._params
+        parts = np.zeros((len(params), 8), np.uint32)
+        if E.presplit_enabled():
+            for i, (p, off) in enumerate(zip(params, self._offsets)):
+                w = p._data
+                if not (E.weight_split_eligible(w) and int(p.size) % (4 * self.world) == 0):
+                    continue
+                n = int(p.size)
+                hi = B.arena_view(self._hi, off, tuple(p.shape))
+                lo = B.arena_view(self._lo, off, tuple(p.shape))
+                sm = B.split_f16(w, out_hi=hi, out_lo=lo)       # binds itself to w
+                self._split[i] = sm
+                amax = np.float32(B.asnumpy(sm.scale)[2])
+                parts[i, :] = amax.view(np.uint32)
+        nb = len(self._buckets)
+        base = 2 * nb * 8 + len(params) * 8                      # parts[1]: read by step 1
+        self._flags[base:base + parts.size] = B.array(parts.reshape(-1))
+        self._p2p_ready = True
+
+    def _launch_p2p(self, b):
+        B, F = self.B, self.F
+        if not self._p2p_ready:
+            self._p2p_prepare()
+        o = self.optim
+        from soket_b200.optim import adam_ratio_bound
+        params = o._params
+        idx = sorted(b.seen)
+        tensors = []
+        for i in idx:
+            p = params[i]
+            if p._data.data_ptr != self._peers_param_ptr(i):
+                raise RuntimeError("DataParallel(mode='p2p'): a parameter's storage was rebound outside the arena "
+                                   "(assign through p.data[...] = value, or close() the DataParallel object first)")
+            start, count = self._shard[i]
+            tensors.append((p._data, self._offsets[i], start, count, self._m[i], self._v[i], self._split[i], i, self._fresh[i]))
+            self._fresh[i] = False
+        rb = adam_ratio_bound(o._beta1, o._beta2, o._t)
+        ub = abs(float(o._lr)) * rb * 1.0001
+        b.ev_ready.record(B.STREAM_COMPUTE)
+        b.ev_ready.wait(B.STREAM_OPT)                # the gradients of this bucket are complete on this rank
+        B.launch_stream(B.STREAM_OPT)
+        try:
+            F.dp_p2p_update(self._peers, b.index, self._step, tensors, o._lr, o._beta1, o._beta2, o._eps,
+                            o._weight_decay if o._have_weight_decay else 0.0, o._one_minus_beta1_t, o._one_minus_beta2_t,
+                            1.0 / self.world, ub, self.share_grads)
+        finally:
+            B.launch_stream(B.STREAM_COMPUTE)
+        b.ev_reduced.record(B.STREAM_OPT)            # this rank's shard of the bucket is updated and published
+        b.launched = True
+        self._n_launch += 1
+        b.t_launch = self._n_launch
+        self._last_bucket = b
+
+    def _peers_param_ptr(self, i):
+        return self._parena.data_ptr + 4 * self._offsets[i]
+
+    def gather_info(self):
+        """What the peer-memory mode holds where (for reports)."""
+        return {"mode": self.mode, "buckets": len(self._buckets), "share_grads": getattr(self, "share_grads", False)}
+
     def _launch(self, b):
         """Queue the bucket's all-reduce (comm stream) and its optimizer update (optimizer stream)."""
+        if self.mode == "p2p":
+            return self._launch_p2p(b)
         B = self.B
         b.ev_ready.record(B.STREAM_COMPUTE)
         b.ev_ready.wait(B.STREAM_COMM)               # the gradients of this bucket are complete
         self.F.nccl_allreduce_on(b.view, B.STREAM_COMM)
         b.ev_reduced.record(B.STREAM_COMM)
+        b.launched = True
+        self._n_launch += 1
+        b.t_launch = self._n_launch
+        self._last_bucket = b
+        if self.opt_overlap:
+            self._update(b, sorted(b.seen))
+
+    def _update(self, b, idx):
+        """The optimizer update of parameters `idx` on the optimizer stream, after bucket b's all-reduce."""
+        B = self.B
         b.ev_reduced.wait(B.STREAM_OPT)
         B.launch_stream(B.STREAM_OPT)
         try:
-            idx = sorted(b.seen)
             self.optim.update(idx)
             # the updated weights' GEMM operand splits, off the critical path too: the next forward
             # finds them cached (engine.linear -> get_split)
@@ -307,8 +475,6 @@ class DataParallel:
                         B.get_split(w)
         finally:
             B.launch_stream(B.STREAM_COMPUTE)
-        b.launched = True
-        self._last_bucket = b
 
     def step(self):
         """The optimizer step of a data-parallel iteration (call after `backward()`)."""
@@ -319,6 +485,20 @@ class DataParallel:
         for b in self._buckets:
             if not b.launched and b.arrived:
                 self._launch(b)
+        if self.mode == "p2p":
+            self.optim.end_step()
+            # the next forward reads weights every OWNER rank has written: wait for all of them (their `done`
+            # also says they have finished reading this rank's gradient slots)
+            self.F.dp_p2p_wait(self._peers, self._step, [b.index for b in self._buckets if b.launched])
+            self._step += 1
+            self._ev_done.record(B.STREAM_COMPUTE)
+            for b in self._buckets:
+                b.arrived, b.launched = 0, False
+                b.seen.clear()
+            return
+        if not self.opt_overlap and self._last_bucket is not None:
+            # NCCL collectives of one communicator complete in issue order: the last one covers them all
+            self._update(self._last_bucket, sorted(i for b in self._buckets if b.launched for i in b.seen))
         B.launch_stream(B.STREAM_OPT)
         try:
             self.optim.end_step()
@@ -335,6 +515,14 @@ class DataParallel:
         recorded on the comm / optimizer streams by the most recent `step()`; for phase timing."""
         return (self._last_bucket.ev_reduced if self._last_bucket is not None else None), self._ev_done
 
+    def bucket_times(self, origin):
+        """[(MB, ms from `origin` until the bucket's gradients were complete, ms until its all-reduce had
+        finished)] of the most recent step, in launch order (call after the step has drained)."""
+        out = []
+        for b in sorted((b for b in self._buckets if b.t_launch >= 0), key=lambda b: b.t_launch):
+            out.append(((b.end - b.start) * 4 / 1e6, origin.elapsed_ms(b.ev_ready), origin.elapsed_ms(b.ev_reduced)))
+        return out
+
     def finish(self):
         """Kept for callers of the round-1 API (`finish(); optim.step()`): reduce whatever is
         pending WITHOUT applying it; the caller's `optim.step()` then updates on the compute stream."""
@@ -350,4 +538,8 @@ class DataParallel:
             for p in self.optim._params:
                 p._grad_buf = None
             self.B.synchronize()
+            if self.mode == "p2p":
+                self.rdv.barrier()                   # nobody unmaps while a peer's kernel may still write here
+                self.F.ipc_close_all()
+                self.rdv.barrier()
             self.F.nccl_destroy()

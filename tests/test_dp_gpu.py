@@ -12,13 +12,18 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("norm,opt,wide", [("layer", "sgd", 0), ("batch", "sgd", 0), ("layer", "adam", 0),
-                                           ("layer", "sgd", 1), ("layer", "adam", 1)])
-def test_two_rank_training_matches_shard_emulation(sk, norm, opt, wide):
+@pytest.mark.parametrize("norm,opt,wide,mode", [("layer", "sgd", 0, "nccl"), ("batch", "sgd", 0, "nccl"),
+                                                ("layer", "adam", 0, "nccl"), ("layer", "sgd", 1, "nccl"),
+                                                ("layer", "adam", 1, "nccl"), ("layer", "adam", 0, "p2p"),
+                                                ("layer", "adam", 1, "p2p"), ("batch", "adam", 0, "p2p")])
+def test_two_rank_training_matches_shard_emulation(sk, norm, opt, wide, mode):
+    """mode nccl: ncclAllReduce per gradient bucket + replicated optimizer; mode p2p: one peer-memory kernel per
+    bucket (reduce-scatter + Adam on the shard + operand split + all-gather, csrc/dp_p2p.cu), which is also
+    compared with the nccl mode over six free-running steps (bit-identical at 2 ranks)."""
     if sk.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt, DP_WIDE=str(wide))
-    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam") + 7 * wide
+    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt, DP_WIDE=str(wide), DP_MODE=mode)
+    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam") + 7 * wide + 13 * (mode == "p2p")
     r = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", str(port),

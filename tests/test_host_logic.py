@@ -170,3 +170,27 @@ def test_adam_ratio_bound_is_a_bound():
                 if sup is not None:
                     assert r <= sup * (1 + 1e-9)
     assert adam_ratio_bound(0.9, 1.0) is None and adam_ratio_bound(0.999, 0.9) is None
+
+
+def test_peer_memory_shards_cover_every_element_once():
+    """soket_b200.dp.shard_of / plan_arena(max_members): host logic of the peer-memory data-parallel update
+    (csrc/dp_p2p.cu): every element of every tensor has exactly one owner rank, equal 16-byte-vector shards
+    where the size allows, one owner otherwise; a bucket never holds more tensors than one launch takes."""
+    from soket_b200.dp import plan_arena, shard_of
+    sizes = [784 * 4096, 4096, 4096 * 4096, 4096, 4096 * 10, 10, 7, 12]
+    for world in (2, 3, 4, 8):
+        for i, n in enumerate(sizes):
+            cover = np.zeros(n, np.int32)
+            owners = 0
+            for r in range(world):
+                start, count = shard_of(n, i, r, world)
+                assert 0 <= start and start + count <= n
+                cover[start:start + count] += 1
+                owners += count > 0
+                if n % (4 * world) == 0:
+                    assert count == n // world and start % 4 == 0
+            assert (cover == 1).all()
+            assert owners == (world if n % (4 * world) == 0 else 1)
+    offsets, total, buckets = plan_arena([10] * 100, 1 << 30, max_members=32)
+    assert [len(m) for _, _, m in buckets] == [32, 32, 32, 4]
+    assert sorted(i for _, _, m in buckets for i in m) == list(range(100))
