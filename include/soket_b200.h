@@ -468,9 +468,9 @@ int sk_nccl_destroy(void);
 
 /* ---- data parallel over NVLink peer memory (no collective library on the data path) ----------------
  * new ("the gradient all-reduce is the only exchange step"; the reference has no
- * multi-GPU code to replace).  One kernel per gradient bucket does reduce-scatter + Adam on this rank's
- * shard + the GEMM weights' fp16x3 operand split + all-gather of the new weights, reading the peers'
- * gradient arenas and writing every replica's parameter / split arenas directly (csrc/dp_p2p.cu).
+ * multi-GPU code to replace).  Per gradient bucket: copy engines pull this rank's shard of the peers'
+ * gradients, one local kernel does the sum + Adam on the shard + the GEMM weights' fp16x3 operand split,
+ * copy engines push the new weights into every replica (csrc/dp_p2p.cu).
  * The arenas (one cudaMalloc block each, same layout on every rank) are exchanged as CUDA IPC handles. */
 #define SK_IPC_HANDLE_BYTES 64
 #define SK_P2P_MAX_WORLD 8
@@ -490,7 +490,7 @@ typedef struct {
 } sk_p2p_peers;
 typedef struct {
     int64_t offset;          /* element offset of the tensor in the arenas */
-    int64_t start, count;    /* this rank's shard of it (count may be 0) */
+    int64_t start, count;    /* the part of it inside this rank's piece of the bucket (count may be 0) */
     float *m, *v;            /* Adam moments of the shard (local, count elements) */
     float *scale4;           /* float[4] of the weight's operand split on THIS rank, or NULL (no split) */
     int slot;                /* row of the parts table (one per tensor) */
@@ -500,10 +500,20 @@ typedef struct {
     double lr, beta1, beta2, eps, weight_decay, one_minus_beta1_t, one_minus_beta2_t, grad_scale, update_bound;
     int share_grads;         /* also leave the reduced gradient (sum over ranks) in every replica's arena */
 } sk_p2p_adam;
-/* on the current launch stream (sk_launch_stream), after the bucket's last gradient kernel in stream order;
- * scratch = SK_P2P_MAX_BUCKETS + n_slots zeroed device words owned by the caller */
-int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int n_tensors,
-                     const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper, unsigned int *scratch);
+/* One bucket = arena elements [bucket_start, bucket_start + bucket_len); rank r owns the piece
+ * [bucket_start + r * L, bucket_start + min((r + 1) * L, bucket_len)) with L = sk_p2p_shard_len(bucket_len, world).
+ * On the current launch stream (sk_launch_stream), after the bucket's last gradient kernel in stream order:
+ * ready flags -> copy engines pull the peers' gradient pieces into `staging` (world * L floats, local) -> one
+ * local kernel (sum in rank order, Adam, operand split) -> copy engines push the piece of params / hi / lo
+ * (/ grads with share_grads) into every replica -> done flags.  `tensors` = the bucket's tensors intersected
+ * with this rank's piece (count 0 where empty); scratch = SK_P2P_MAX_BUCKETS + n_slots zeroed device words. */
+int64_t sk_p2p_shard_len(int64_t bucket_len, int world);
+int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
+                     float *staging, int n_tensors, const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper,
+                     unsigned int *scratch);
+/* copy-engine probe between two device buffers (either may be a peer mapping from sk_ipc_open): reps x n_copies
+ * cudaMemcpyAsync of `bytes` each, round-robin over n_streams streams; *ms = CUDA-event time of the batch */
+int sk_p2p_copy_probe(void *dst, const void *src, size_t bytes, int n_copies, int n_streams, int reps, float *ms);
 /* the current launch stream waits until every peer has finished `step` on the buckets in the mask */
 int sk_dp_p2p_wait(const unsigned int *flags, int n_buckets, int world, unsigned int step, const unsigned int *bucket_mask);
 

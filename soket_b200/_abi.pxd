@@ -299,6 +299,9 @@ cdef extern from "soket_b200.h" nogil:
         double grad_scale
         double update_bound
         int share_grads
-    int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int n_tensors,
-                         const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper, unsigned int *scratch)
+    int64_t sk_p2p_shard_len(int64_t bucket_len, int world)
+    int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
+                         float *staging, int n_tensors, const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper,
+                         unsigned int *scratch)
     int sk_dp_p2p_wait(const unsigned int *flags, int n_buckets, int world, unsigned int step, const unsigned int *bucket_mask)
+    int sk_p2p_copy_probe(void *dst, const void *src, size_t nbytes, int n_copies, int n_streams, int reps, float *ms)

@@ -467,6 +467,13 @@ def ipc_close_all():
     _check(sk_ipc_close_all())
 
 
+def p2p_copy_probe(size_t dst, size_t src, size_t nbytes, int n_copies=1, int n_streams=1, int reps=1):
+    """Milliseconds for reps x n_copies copy-engine copies of nbytes each between two device addresses."""
+    cdef float ms = 0
+    _check(sk_p2p_copy_probe(<void *> dst, <const void *> src, nbytes, n_copies, n_streams, reps, &ms))
+    return ms
+
+
 cdef class P2pPeers:
     """The arenas of every rank as this process sees them (soket_b200.dp, mode 'p2p')."""
     cdef sk_p2p_peers c
@@ -493,11 +500,17 @@ cdef class P2pPeers:
         self.scratch = _B.zeros((256 + max(n_slots, 1),), 'uint32')
 
 
-def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, list tensors, double lr, double beta1, double beta2,
+def p2p_shard_len(int64_t bucket_len, int world):
+    return int(sk_p2p_shard_len(bucket_len, world))
+
+
+def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
+                  ndarray staging, list tensors, double lr, double beta1, double beta2,
                   double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
                   double grad_scale, double update_bound, bint share_grads):
     """One bucket of the peer-memory data-parallel Adam step (sk_dp_p2p_update) on the current launch stream.
-    tensors: [(param ndarray, arena offset, shard start, shard count, m, v, SplitMat or None, slot, first)]."""
+    tensors: [(param ndarray, arena offset, start, count, m, v, SplitMat or None, slot, first)] -- start / count =
+    the part of the tensor inside this rank's piece of the bucket; staging: world * shard_len float32 (local)."""
     cdef int n = len(tensors), i
     cdef sk_p2p_tensor *ts = <sk_p2p_tensor *> malloc(max(n, 1) * sizeof(sk_p2p_tensor))
     if ts == NULL:
@@ -519,7 +532,10 @@ def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, list tensors, d
                 sm = <SplitMat> split
                 ts[i].scale4 = <float *> sm.scale._ptr
             ts[i].slot = slot; ts[i].first = 1 if first else 0
-        _check(sk_dp_p2p_update(&peers.c, bucket, step, n, ts, &h, <unsigned int *> peers.scratch._ptr))
+        if staging._code != SK_F32 or staging._numel() < peers.c.world * sk_p2p_shard_len(bucket_len, peers.c.world):
+            raise ValueError('dp_p2p_update: staging must hold world * shard_len float32 elements')
+        _check(sk_dp_p2p_update(&peers.c, bucket, step, bucket_start, bucket_len, _fptr(staging), n, ts, &h,
+                                <unsigned int *> peers.scratch._ptr))
     finally:
         free(ts)
     for i in range(n):

@@ -1,27 +1,31 @@
-// dp_p2p.cu -- data-parallel Adam as ONE kernel per gradient bucket over NVLink peer memory:
-// reduce-scatter of the gradients + Adam on this rank's shard + fp16x3 operand split + all-gather of the
-// new weights, with no collective library on the data path.
+// dp_p2p.cu -- data-parallel Adam over NVLink peer memory, no collective library on the data path:
+// per gradient bucket, copy engines pull this rank's shard of every peer's gradients, ONE local kernel does
+// the W-term sum + Adam on the shard + the GEMM weights' fp16x3 operand split, and copy engines push the new
+// weights (fp32 + hi / lo) into every replica -- reduce-scatter + optimizer + all-gather with the SMs touching
+// only local HBM, and 1/W of the replicated update's optimizer traffic.
 //
 // New relative to the reference (it has no collective at all).  Every rank maps
 // its peers' arenas with CUDA IPC (one cudaMalloc block each, same layout on every rank):
-//   G   fp32 gradients (the slots backward writes into)         read  from all peers, shard only
-//   P   fp32 parameters (the tensors' own storage)              written to all peers, shard only
-//   HI, LO  fp16 hi / lo operand split of the Linear weights    written to all peers, shard only
+//   G   fp32 gradients (the slots backward writes into)         pulled from all peers, shard only
+//   P   fp32 parameters (the tensors' own storage)              pushed to all peers, shard only
+//   HI, LO  fp16 hi / lo operand split of the Linear weights    pushed to all peers, shard only
 //   F   uint32 flags: ready[bucket][rank], done[bucket][rank], |max| parts[2][tensor][rank]
-// A tensor of n elements is cut into `world` equal shards (n % (4 world) == 0; anything else has ONE owner
-// rank).  The owner of a shard sums the `world` gradient shards in rank order (so the result does not depend
-// on who computes it), applies the optimizer's element update (optim.cuh: the reference's arithmetic), and
-// stores the new weights -- and, for GEMM weights, their hi / lo split under a power-of-two scale every rank
-// derives from the same numbers: max over ranks of last step's shard |max| + the optimizer's update bound --
-// into all `world` replicas.  Per step and GPU: 7/8 of the gradient bytes come in over NVLink, 7/8 of
-// (4 + 4) B/element go out, and the optimizer state traffic is 1/world of the replicated update's.
+// A bucket's arena range is cut into `world` contiguous shards of a multiple of 64 elements.  The owner of a
+// shard sums the `world` gradient shards in rank order (so the result does not depend on who computes it),
+// applies the optimizer's element update (optim.cuh: the reference's arithmetic) and emits, for GEMM weights,
+// the hi / lo split under a power-of-two scale every rank derives from the same numbers: max over ranks of
+// last step's shard |max| + the optimizer's update bound.  Why copy engines: an SM sustains only a few GB/s
+// of remote loads / stores (measured: 96 CTAs of direct peer ld/st moved 370 GB/s and fought the backward
+// GEMMs for SMs), a copy engine moves 8 MB shards at 520-560 GB/s beside them (profiles/r2_p2p_copy_bench.txt).
 //
-// Synchronisation (flags live in peer-mapped memory, values = step number, monotonic):
-//   ready: a 1-block kernel on the optimizer stream, stream-ordered after the bucket's last gradient kernel,
-//          stores `step` into every peer's ready[bucket][me], then spins until its own ready[bucket][*] == step.
-//   done:  the update kernel's last block (threadfence_system + counter) stores `step` into every peer's
+// Streams per bucket: S0 (the caller's launch stream: ready kernel, update kernel), one pull stream, two push
+// streams, one flag stream; events chain them, S0 never waits for the pushes (bucket k+1's pull overlaps
+// bucket k's push).  Flags live in peer-mapped memory, values = step number, monotonic:
+//   ready: a 1-block kernel on S0, stream-ordered after the bucket's last gradient kernel, stores `step` into
+//          every peer's ready[bucket][me], then spins until its own ready[bucket][*] == step.
+//   done:  a 1-block kernel on the flag stream, after this rank's pushes, stores `step` into every peer's
 //          done[bucket][me]; sk_dp_p2p_wait (1 block on the compute stream) spins on done[*][*] before the
-//          next forward reads the weights.  A peer's `done` also means it has finished READING this rank's
+//          next forward reads the weights.  A peer's `done` also means it has finished PULLING this rank's
 //          gradient shard, so the next backward may overwrite the slots.
 #include <cuda.h>
 #include <stdlib.h>
@@ -54,17 +58,17 @@ struct P2pTensor {
 };
 
 struct P2pArgs {
-  float *G[SK_P2P_MAX_WORLD];
-  float *P[SK_P2P_MAX_WORLD];
-  __half *HI[SK_P2P_MAX_WORLD];
-  __half *LO[SK_P2P_MAX_WORLD];
+  float *G, *P;                        // this rank's arenas
+  __half *HI, *LO;
+  const float *S;                      // staging: peer q's copy of this rank's shard at S + q * shard_stride
+  int64_t shard_start, shard_stride;   // first arena element of this rank's shard; elements between staged copies
   unsigned int *F[SK_P2P_MAX_WORLD];
   P2pTensor t[kP2pMaxTensors];
   int block_start[kP2pMaxTensors + 1];
   int n, total_blocks, world, rank, bucket;
   unsigned int step;
   int done_off, parts_off, n_slots;    // offsets (in words) into F
-  int share_grads;                     // also store the reduced gradient into every replica's G
+  int share_grads;                     // also leave the reduced gradient in G (the caller pushes it to the replicas)
   float bc1, bc2, update_bound;
   P2pHyper h;
   unsigned int *counter;               // local: finished blocks of this launch (zero before and after)
@@ -150,69 +154,58 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_adam_kernel(const __grid_cons
     float amax = 0.f;
     const bool vec = ((T.count | T.start) & 3) == 0;
     if (vec) {
-      // all the remote reads of this block-iteration first (4 x world 16-byte loads in flight per thread: NVLink
-      // latency is ~2 us), then the updates and the replica stores
-      float4 gs[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t i = base + ((int64_t)j * kP2pThreads + threadIdx.x) * 4;
-        gs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < T.count) {
           const int64_t e = e0 + i;
-          float4 g = ld_peer(a.G[0] + e);
-          for (int q = 1; q < W; ++q) {
-            const float4 x = ld_peer(a.G[q] + e);
-            g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w);
+          const int64_t k = e - a.shard_start;            // element of the shard (staging index)
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < W; ++q) {                   // rank order whoever owns the shard
+            const float4 x = q == a.rank ? ld_stream(reinterpret_cast<const float4 *>(a.G + e))
+                                         : ld_stream(reinterpret_cast<const float4 *>(a.S + q * a.shard_stride + k));
+            if (q == 0) g = x;
+            else { g.x = __fadd_rn(g.x, x.x); g.y = __fadd_rn(g.y, x.y); g.z = __fadd_rn(g.z, x.z); g.w = __fadd_rn(g.w, x.w); }
           }
-          gs[j] = g;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t i = base + ((int64_t)j * kP2pThreads + threadIdx.x) * 4;
-        if (i < T.count) {
-          const int64_t e = e0 + i;
-          float4 g = gs[j];
-          float4 pv = *reinterpret_cast<const float4 *>(a.P[a.rank] + e);
+          float4 pv = *reinterpret_cast<const float4 *>(a.P + e);
           float4 mv = h.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4 *>(T.m + i);
           float4 vv = h.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4 *>(T.v + i);
+          if (a.share_grads) *reinterpret_cast<float4 *>(a.G + e) = g;
           adam_one(pv.x, g.x, mv.x, vv.x, h, a.bc1, a.bc2); adam_one(pv.y, g.y, mv.y, vv.y, h, a.bc1, a.bc2);
           adam_one(pv.z, g.z, mv.z, vv.z, h, a.bc1, a.bc2); adam_one(pv.w, g.w, mv.w, vv.w, h, a.bc1, a.bc2);
           amax = fmaxf(fmaxf(amax, fmaxf(fabsf(pv.x), fabsf(pv.y))), fmaxf(fabsf(pv.z), fabsf(pv.w)));
           *reinterpret_cast<float4 *>(T.m + i) = mv;
           *reinterpret_cast<float4 *>(T.v + i) = vv;
-          uint2 hh, ll;
-          if (split) split4(pv, sc, hh, ll);
-          for (int q = 0; q < W; ++q) {
-            const int peer = (a.rank + q) % W;    // every rank starts with its own replica: spreads the link load
-            *reinterpret_cast<float4 *>(a.P[peer] + e) = pv;
-            if (split) {
-              *reinterpret_cast<uint2 *>(a.HI[peer] + e) = hh;
-              *reinterpret_cast<uint2 *>(a.LO[peer] + e) = ll;
-            }
-            if (a.share_grads) *reinterpret_cast<float4 *>(a.G[peer] + e) = g;
+          *reinterpret_cast<float4 *>(a.P + e) = pv;
+          if (split) {
+            uint2 hh, ll;
+            split4(pv, sc, hh, ll);
+            *reinterpret_cast<uint2 *>(a.HI + e) = hh;
+            *reinterpret_cast<uint2 *>(a.LO + e) = ll;
           }
         }
       }
     } else {
       for (int64_t i = base + threadIdx.x; i < T.count && i < base + kP2pChunk; i += kP2pThreads) {
         const int64_t e = e0 + i;
-        float g = ld_peer1(a.G[0] + e);
-        for (int q = 1; q < W; ++q) g = __fadd_rn(g, ld_peer1(a.G[q] + e));
-        float pv = a.P[a.rank][e];
+        const int64_t k = e - a.shard_start;
+        float g = 0.f;
+        for (int q = 0; q < W; ++q) {
+          const float x = q == a.rank ? a.G[e] : a.S[q * a.shard_stride + k];
+          g = q == 0 ? x : __fadd_rn(g, x);
+        }
+        float pv = a.P[e];
         float mv = h.first ? 0.f : T.m[i], vv = h.first ? 0.f : T.v[i];
+        if (a.share_grads) a.G[e] = g;
         adam_one(pv, g, mv, vv, h, a.bc1, a.bc2);
         amax = fmaxf(amax, fabsf(pv));
         T.m[i] = mv; T.v[i] = vv;
-        for (int q = 0; q < W; ++q) {
-          a.P[q][e] = pv;
-          if (split) {
-            const float x = pv * sc;
-            const __half hv = __float2half_rn(x);
-            a.HI[q][e] = hv;
-            a.LO[q][e] = __float2half_rn(x - __half2float(hv));
-          }
-          if (a.share_grads) a.G[q][e] = g;
+        a.P[e] = pv;
+        if (split) {
+          const float x = pv * sc;
+          const __half hv = __float2half_rn(x);
+          a.HI[e] = hv;
+          a.LO[e] = __float2half_rn(x - __half2float(hv));
         }
       }
     }
@@ -223,9 +216,9 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_adam_kernel(const __grid_cons
       if (bits > *(volatile unsigned int *)acc) atomicMax(acc, bits);
     }
   }
-  // all of this block's stores (local and peer) before the counter; the last block publishes
+  // the last block publishes the shard maxima to every rank's parts table for the next step
   __shared__ bool last;
-  __threadfence_system();
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
   __syncthreads();
@@ -241,8 +234,15 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_adam_kernel(const __grid_cons
   __threadfence_system();
   __syncthreads();
   for (int t = threadIdx.x; t < a.n; t += kP2pThreads) a.amax_acc[a.t[t].slot] = 0u;
-  if (threadIdx.x < W) st_release_sys(a.F[threadIdx.x] + a.done_off + a.bucket * SK_P2P_MAX_WORLD + a.rank, a.step);
   if (threadIdx.x == 0) *a.counter = 0u;
+}
+
+// after this rank's pushes of the bucket (stream order): tell every peer
+__global__ void p2p_done_kernel(const __grid_constant__ P2pReadyArgs a) {
+  if ((int)threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(a.F[threadIdx.x] + a.ready_off + a.bucket * SK_P2P_MAX_WORLD + a.rank, a.step);   // ready_off = done_off here
+  }
 }
 
 struct P2pWaitArgs {
@@ -322,18 +322,57 @@ int sk_ipc_close_all(void) {
   return SK_OK;
 }
 
-int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int n_tensors,
-                     const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper, unsigned int *scratch) {
+// streams and events of the peer-memory update (created on first use)
+struct P2pStreams {
+  cudaStream_t pull = nullptr, push[2] = {nullptr, nullptr}, flag = nullptr;
+  static constexpr int kRing = 64;
+  cudaEvent_t ready[kRing], pulled[kRing], updated[kRing], pushed[kRing][2];
+  unsigned int next = 0;
+  bool ok = false;
+};
+static P2pStreams g_p2p;
+
+static int p2p_streams_init() {
+  if (g_p2p.ok) return SK_OK;
+  // the transfers must not queue behind compute: highest priority
+  int lo = 0, hi = 0;
+  SK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.pull, cudaStreamNonBlocking, hi));
+  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.push[0], cudaStreamNonBlocking, hi));
+  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.push[1], cudaStreamNonBlocking, hi));
+  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.flag, cudaStreamNonBlocking, hi));
+  for (int i = 0; i < P2pStreams::kRing; ++i) {
+    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.ready[i], cudaEventDisableTiming));
+    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pulled[i], cudaEventDisableTiming));
+    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.updated[i], cudaEventDisableTiming));
+    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pushed[i][0], cudaEventDisableTiming));
+    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pushed[i][1], cudaEventDisableTiming));
+  }
+  g_p2p.ok = true;
+  return SK_OK;
+}
+
+int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
+                     float *staging, int n_tensors, const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper,
+                     unsigned int *scratch) {
   int rc;
   if ((rc = ensure_init())) return rc;
-  SK_REQUIRE(peers && tensors && hyper && scratch, "sk_dp_p2p_update: null argument");
+  SK_REQUIRE(peers && tensors && hyper && scratch && staging, "sk_dp_p2p_update: null argument");
   SK_REQUIRE(peers->world >= 2 && peers->world <= SK_P2P_MAX_WORLD && peers->rank >= 0 && peers->rank < peers->world,
              "sk_dp_p2p_update: bad rank %d / world %d", peers->rank, peers->world);
   SK_REQUIRE(bucket >= 0 && bucket < peers->n_buckets && peers->n_buckets <= SK_P2P_MAX_BUCKETS && step >= 1,
              "sk_dp_p2p_update: bad bucket %d / step %u", bucket, step);
   SK_REQUIRE(n_tensors >= 1 && n_tensors <= kP2pMaxTensors, "sk_dp_p2p_update: 1..%d tensors per bucket (got %d)",
              kP2pMaxTensors, n_tensors);
-  const int W = peers->world;
+  SK_REQUIRE(bucket_start >= 0 && bucket_len > 0 && bucket_start % 64 == 0, "sk_dp_p2p_update: bad bucket range");
+  if ((rc = p2p_streams_init())) return rc;
+  const int W = peers->world, R = peers->rank;
+  // this rank's shard of the bucket: `world` contiguous pieces of a multiple of 64 elements (the last may be short / empty)
+  const int64_t stride = sk_p2p_shard_len(bucket_len, W);
+  const int64_t my_start = bucket_start + (int64_t)R * stride;
+  int64_t my_len = bucket_start + bucket_len - my_start;
+  if (my_len > stride) my_len = stride;
+  if (my_len < 0) my_len = 0;
   const int ready_off = 0, done_off = peers->n_buckets * SK_P2P_MAX_WORLD;
   const int parts_off = 2 * peers->n_buckets * SK_P2P_MAX_WORLD;
   P2pReadyArgs r;
@@ -342,32 +381,37 @@ int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, i
   memset(&a, 0, sizeof(a));
   for (int q = 0; q < W; ++q) {
     SK_REQUIRE(peers->grads[q] && peers->params[q] && peers->flags[q], "sk_dp_p2p_update: peer %d has a null arena", q);
-    a.G[q] = peers->grads[q]; a.P[q] = peers->params[q];
-    a.HI[q] = (__half *)peers->hi[q]; a.LO[q] = (__half *)peers->lo[q];
     a.F[q] = peers->flags[q]; r.F[q] = peers->flags[q];
   }
+  a.G = peers->grads[R]; a.P = peers->params[R];
+  a.HI = (__half *)peers->hi[R]; a.LO = (__half *)peers->lo[R];
+  a.S = staging; a.shard_start = my_start; a.shard_stride = stride;
   int blocks = 0;
+  bool any_split = false;
   double elems = 0, split_elems = 0;
   for (int i = 0; i < n_tensors; ++i) {
     const sk_p2p_tensor &s = tensors[i];
     SK_REQUIRE(s.offset >= 0 && s.start >= 0 && s.count >= 0 && s.slot >= 0 && s.slot < peers->n_slots,
                "sk_dp_p2p_update: tensor %d has a bad range / slot", i);
     SK_REQUIRE(s.count == 0 || (s.m && s.v), "sk_dp_p2p_update: tensor %d has no optimizer state arrays", i);
+    SK_REQUIRE(s.count == 0 || (s.offset + s.start >= my_start && s.offset + s.start + s.count <= my_start + my_len),
+               "sk_dp_p2p_update: tensor %d: [%lld, +%lld) is outside this rank's shard of the bucket", i,
+               (long long)(s.offset + s.start), (long long)s.count);
     SK_REQUIRE(!s.scale4 || (peers->hi[0] && peers->lo[0]), "sk_dp_p2p_update: tensor %d wants a split but there is no hi / lo arena", i);
     P2pTensor &T = a.t[i];
     T.off = s.offset; T.start = s.start; T.count = s.count; T.m = s.m; T.v = s.v; T.scale4 = s.scale4;
     T.slot = s.slot; T.first = s.first;
     if (((s.count | s.start) & 3) == 0)
-      SK_REQUIRE(s.count == 0 || (((uintptr_t)s.m | (uintptr_t)s.v) & 15) == 0 && (s.offset & 3) == 0,
+      SK_REQUIRE(s.count == 0 || ((((uintptr_t)s.m | (uintptr_t)s.v) & 15) == 0 && (s.offset & 3) == 0),
                  "sk_dp_p2p_update: tensor %d: vector path needs 16-byte aligned state and arena offset", i);
     a.block_start[i] = blocks;
     blocks += (int)((s.count + kP2pChunk - 1) / kP2pChunk);
     elems += (double)s.count;
-    if (s.scale4) split_elems += (double)s.count;
+    if (s.scale4) { split_elems += (double)s.count; any_split = true; }
     r.slot[i] = s.slot; r.scale4[i] = s.scale4;
   }
   a.block_start[n_tensors] = blocks;
-  a.n = n_tensors; a.total_blocks = blocks; a.world = W; a.rank = peers->rank; a.bucket = bucket; a.step = step;
+  a.n = n_tensors; a.total_blocks = blocks; a.world = W; a.rank = R; a.bucket = bucket; a.step = step;
   a.done_off = done_off; a.parts_off = parts_off; a.n_slots = peers->n_slots;
   a.share_grads = hyper->share_grads;
   a.bc1 = (float)hyper->one_minus_beta1_t; a.bc2 = (float)hyper->one_minus_beta2_t;
@@ -378,20 +422,105 @@ int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, i
   a.h.have_wd = hyper->weight_decay != 0.0; a.h.have_scale = hyper->grad_scale != 1.0; a.h.first = 0;
   a.counter = scratch + bucket;                       // one counter per bucket: launches of different buckets may overlap
   a.amax_acc = scratch + SK_P2P_MAX_BUCKETS;
-  r.world = W; r.rank = peers->rank; r.bucket = bucket; r.ready_off = ready_off; r.parts_off = parts_off;
+  r.world = W; r.rank = R; r.bucket = bucket; r.ready_off = ready_off; r.parts_off = parts_off;
   r.n_slots = peers->n_slots; r.step = step; r.n = n_tensors; r.update_bound = a.update_bound;
-  p2p_ready_kernel<<<1, 32, 0, stream()>>>(r);
+  cudaStream_t s0 = stream();
+  const unsigned int slot = g_p2p.next++ % P2pStreams::kRing;
+  // 1. every rank's gradients of this bucket are complete
+  p2p_ready_kernel<<<1, 32, 0, s0>>>(r);
   SK_LAUNCH_CHECK();
-  // a bounded persistent grid: enough warps to keep the NVLink reads in flight, few enough to sit beside the
-  // GEMM CTAs of backward (SOKET_B200_P2P_GRID = blocks, default 2 per SM)
-  static const int grid_env = getenv("SOKET_B200_P2P_GRID") ? atoi(getenv("SOKET_B200_P2P_GRID")) : 0;
-  int grid = grid_env > 0 ? grid_env : 2 * ctx().num_sms;
-  if (grid > blocks) grid = blocks;
-  if (grid < 1) grid = 1;                             // a rank without a shard of this bucket still signals `done`
-  // per element of the shard: world gradient reads, p / m / v read + write, world replicas of p (+ hi / lo) written
-  ProfScope ps(SK_PROF_OPTIM, elems * (4.0 * W + 20.0 + 4.0 * W + (a.share_grads ? 4.0 * W : 0.0)) + split_elems * 4.0 * W);
-  p2p_adam_kernel<<<grid, kP2pThreads, 0, stream()>>>(a);
+  // 2. copy engines pull this rank's shard of every peer's gradients into the staging rows
+  if (my_len > 0) {
+    SK_CUDA(cudaEventRecord(g_p2p.ready[slot], s0));
+    SK_CUDA(cudaStreamWaitEvent(g_p2p.pull, g_p2p.ready[slot], 0));
+    for (int k = 1; k < W; ++k) {
+      const int q = (R + k) % W;                      // every rank starts with a different peer
+      SK_CUDA(cudaMemcpyAsync(staging + (int64_t)q * stride, peers->grads[q] + my_start, (size_t)my_len * 4,
+                              cudaMemcpyDefault, g_p2p.pull));
+    }
+    SK_CUDA(cudaEventRecord(g_p2p.pulled[slot], g_p2p.pull));
+    SK_CUDA(cudaStreamWaitEvent(s0, g_p2p.pulled[slot], 0));
+  }
+  // 3. the local update: sum in rank order, Adam, operand split, shard maxima to every rank's parts table
+  {
+    static const int grid_env = getenv("SOKET_B200_P2P_GRID") ? atoi(getenv("SOKET_B200_P2P_GRID")) : 0;
+    int grid = grid_env > 0 ? grid_env : 2 * ctx().num_sms;
+    if (grid > blocks) grid = blocks;
+    if (grid < 1) grid = 1;                           // a rank without a shard still publishes (zero) maxima
+    // per element of the shard: world gradient reads, p / m / v read + write, hi / lo written
+    ProfScope ps(SK_PROF_OPTIM, elems * (4.0 * W + 24.0 + (a.share_grads ? 4.0 : 0.0)) + split_elems * 4.0);
+    p2p_adam_kernel<<<grid, kP2pThreads, 0, s0>>>(a);
+    SK_LAUNCH_CHECK();
+  }
+  // 4. copy engines push the shard of the new weights (and their split) into every replica; S0 does not wait
+  SK_CUDA(cudaEventRecord(g_p2p.updated[slot], s0));
+  for (int h = 0; h < 2; ++h) SK_CUDA(cudaStreamWaitEvent(g_p2p.push[h], g_p2p.updated[slot], 0));
+  if (my_len > 0) {
+    for (int k = 1; k < W; ++k) {
+      const int q = (R + k) % W;
+      cudaStream_t ps = g_p2p.push[k & 1];
+      SK_CUDA(cudaMemcpyAsync(peers->params[q] + my_start, peers->params[R] + my_start, (size_t)my_len * 4,
+                              cudaMemcpyDefault, ps));
+      if (any_split) {
+        SK_CUDA(cudaMemcpyAsync((__half *)peers->hi[q] + my_start, (const __half *)peers->hi[R] + my_start,
+                                (size_t)my_len * 2, cudaMemcpyDefault, ps));
+        SK_CUDA(cudaMemcpyAsync((__half *)peers->lo[q] + my_start, (const __half *)peers->lo[R] + my_start,
+                                (size_t)my_len * 2, cudaMemcpyDefault, ps));
+      }
+      if (a.share_grads)
+        SK_CUDA(cudaMemcpyAsync(peers->grads[q] + my_start, peers->grads[R] + my_start, (size_t)my_len * 4,
+                                cudaMemcpyDefault, ps));
+    }
+  }
+  // 5. done[bucket][me] on every rank once both push streams have drained
+  for (int h = 0; h < 2; ++h) {
+    SK_CUDA(cudaEventRecord(g_p2p.pushed[slot][h], g_p2p.push[h]));
+    SK_CUDA(cudaStreamWaitEvent(g_p2p.flag, g_p2p.pushed[slot][h], 0));
+  }
+  P2pReadyArgs d = r;
+  d.ready_off = done_off;
+  p2p_done_kernel<<<1, 32, 0, g_p2p.flag>>>(d);
   SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+int64_t sk_p2p_shard_len(int64_t bucket_len, int world) {
+  if (world < 1 || bucket_len <= 0) return 0;
+  const int64_t per = (bucket_len + world - 1) / world;
+  return (per + 63) / 64 * 64;
+}
+
+// copy-engine probe: `reps` x `n_copies` cudaMemcpyAsync of `bytes` each, copy k on stream k % n_streams,
+// dst / src advance by `bytes` per copy; CUDA-event time of the whole batch in *ms
+int sk_p2p_copy_probe(void *dst, const void *src, size_t bytes, int n_copies, int n_streams, int reps, float *ms) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(dst && src && ms && bytes > 0 && n_copies >= 1 && n_streams >= 1 && n_streams <= 8 && reps >= 1,
+             "sk_p2p_copy_probe: bad argument");
+  static cudaStream_t st[8] = {nullptr};
+  static cudaEvent_t e0 = nullptr, e1 = nullptr, fin[8] = {nullptr};
+  if (!e0) {
+    SK_CUDA(cudaEventCreate(&e0));
+    SK_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 8; ++i) {
+      SK_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+      SK_CUDA(cudaEventCreateWithFlags(&fin[i], cudaEventDisableTiming));
+    }
+  }
+  SK_CUDA(cudaDeviceSynchronize());
+  SK_CUDA(cudaEventRecord(e0, st[0]));
+  for (int i = 1; i < n_streams; ++i) SK_CUDA(cudaStreamWaitEvent(st[i], e0, 0));
+  for (int r = 0; r < reps; ++r)
+    for (int k = 0; k < n_copies; ++k)
+      SK_CUDA(cudaMemcpyAsync((char *)dst + (size_t)k * bytes, (const char *)src + (size_t)k * bytes, bytes,
+                              cudaMemcpyDefault, st[k % n_streams]));
+  for (int i = 1; i < n_streams; ++i) {
+    SK_CUDA(cudaEventRecord(fin[i], st[i]));
+    SK_CUDA(cudaStreamWaitEvent(st[0], fin[i], 0));
+  }
+  SK_CUDA(cudaEventRecord(e1, st[0]));
+  SK_CUDA(cudaEventSynchronize(e1));
+  SK_CUDA(cudaEventElapsedTime(ms, e0, e1));
   return SK_OK;
 }
 

@@ -160,14 +160,23 @@ class Rendezvous:
             shutil.rmtree(self.dir, ignore_errors=True)
 
 
-def shard_of(n: int, index: int, rank: int, world: int):
-    """(start, count) of rank's shard of parameter number `index` with n elements under the peer-memory
-    update: `world` equal shards when n splits into whole 16-byte vectors per rank, else the whole tensor
-    on ONE owner rank (index % world) and nothing on the others.  Pure host logic (CPU-tested)."""
-    if n % (4 * world) == 0:
-        c = n // world
-        return rank * c, c
-    return (0, n) if rank == index % world else (0, 0)
+def shard_len(bucket_len: int, world: int) -> int:
+    """Elements per rank of a bucket under the peer-memory update: ceil(len / world) rounded up to 64 elements
+    (mirrors sk_p2p_shard_len)."""
+    if bucket_len <= 0:
+        return 0
+    per = (bucket_len + world - 1) // world
+    return (per + 63) // 64 * 64
+
+
+def piece_of(bucket_start: int, bucket_len: int, offset: int, n: int, rank: int, world: int):
+    """(start, count): the part of a tensor of n elements at arena offset `offset` that falls into rank's
+    contiguous piece of the bucket [bucket_start, bucket_start + bucket_len).  Pure host logic (CPU-tested)."""
+    L = shard_len(bucket_len, world)
+    lo = bucket_start + rank * L
+    hi = min(lo + L, bucket_start + bucket_len)
+    a, b = max(lo, offset), min(hi, offset + n)
+    return (a - offset, b - a) if b > a else (0, 0)
 
 
 def exchange_unique_id(rdv: Rendezvous, make_id) -> bytes:
@@ -360,11 +369,16 @@ class DataParallel:
             view = B.arena_view(self._parena, off, tuple(p.shape))
             view[...] = p._data
             p._data = view                                      # the tensor's storage IS its window of the arena
-            start, count = shard_of(int(p.size), i, rank, world)
-            self._shard[i] = (start, count)
-            if count:
-                self._m[i] = B.zeros((count,), "float32")
-                self._v[i] = B.zeros((count,), "float32")
+        stage = 0
+        for b in self._buckets:
+            stage = max(stage, world * shard_len(b.end - b.start, world))
+            for i in b.members:
+                start, count = piece_of(b.start, b.end - b.start, self._offsets[i], int(params[i].size), rank, world)
+                self._shard[i] = (start, count)
+                if count:
+                    self._m[i] = B.zeros((count,), "float32")
+                    self._v[i] = B.zeros((count,), "float32")
+        self._staging = B.zeros((max(stage, 1),), "float32")    # world rows of one bucket shard (buckets run in order)
         B.synchronize()
         mine = [F.ipc_export(a) for a in (self.arena, self._parena, self._hi, self._lo, self._flags)]
         everyone = [pickle.loads(x) for x in rdv.all_gather_bytes(pickle.dumps(mine))]
@@ -385,7 +399,7 @@ class DataParallel:
         if E.presplit_enabled():
             for i, (p, off) in enumerate(zip(params, self._offsets)):
                 w = p._data
-                if not (E.weight_split_eligible(w) and int(p.size) % (4 * self.world) == 0):
+                if not E.weight_split_eligible(w):
                     continue
                 n = int(p.size)
                 hi = B.arena_view(self._hi, off, tuple(p.shape))
@@ -406,9 +420,11 @@ class DataParallel:
         o = self.optim
         from soket_b200.optim import adam_ratio_bound
         params = o._params
-        idx = sorted(b.seen)
+        if len(b.seen) != len(b.members):
+            raise RuntimeError("DataParallel(mode='p2p'): a parameter of this bucket received no gradient in this step "
+                               "(every rank must update the same tensors); use mode='nccl' for such models")
         tensors = []
-        for i in idx:
+        for i in b.members:
             p = params[i]
             if p._data.data_ptr != self._peers_param_ptr(i):
                 raise RuntimeError("DataParallel(mode='p2p'): a parameter's storage was rebound outside the arena "
@@ -422,7 +438,7 @@ class DataParallel:
         b.ev_ready.wait(B.STREAM_OPT)                # the gradients of this bucket are complete on this rank
         B.launch_stream(B.STREAM_OPT)
         try:
-            F.dp_p2p_update(self._peers, b.index, self._step, tensors, o._lr, o._beta1, o._beta2, o._eps,
+            F.dp_p2p_update(self._peers, b.index, self._step, b.start, b.end - b.start, self._staging, tensors, o._lr, o._beta1, o._beta2, o._eps,
                             o._weight_decay if o._have_weight_decay else 0.0, o._one_minus_beta1_t, o._one_minus_beta2_t,
                             1.0 / self.world, ub, self.share_grads)
         finally:

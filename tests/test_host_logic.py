@@ -173,24 +173,29 @@ def test_adam_ratio_bound_is_a_bound():
 
 
 def test_peer_memory_shards_cover_every_element_once():
-    """soket_b200.dp.shard_of / plan_arena(max_members): host logic of the peer-memory data-parallel update
-    (csrc/dp_p2p.cu): every element of every tensor has exactly one owner rank, equal 16-byte-vector shards
-    where the size allows, one owner otherwise; a bucket never holds more tensors than one launch takes."""
-    from soket_b200.dp import plan_arena, shard_of
+    """soket_b200.dp.piece_of / shard_len / plan_arena(max_members): host logic of the peer-memory data-parallel
+    update (csrc/dp_p2p.cu): a bucket's arena range is cut into `world` contiguous pieces of a multiple of 64
+    elements; every element of every tensor falls into exactly one rank's piece; a bucket never holds more
+    tensors than one launch takes."""
+    from soket_b200.dp import piece_of, plan_arena, shard_len
     sizes = [784 * 4096, 4096, 4096 * 4096, 4096, 4096 * 10, 10, 7, 12]
     for world in (2, 3, 4, 8):
-        for i, n in enumerate(sizes):
-            cover = np.zeros(n, np.int32)
-            owners = 0
-            for r in range(world):
-                start, count = shard_of(n, i, r, world)
-                assert 0 <= start and start + count <= n
-                cover[start:start + count] += 1
-                owners += count > 0
-                if n % (4 * world) == 0:
-                    assert count == n // world and start % 4 == 0
-            assert (cover == 1).all()
-            assert owners == (world if n % (4 * world) == 0 else 1)
+        for bucket_floats in (1 << 10, 1 << 22, 1 << 30):
+            offsets, total, buckets = plan_arena(sizes, bucket_floats, max_members=32)
+            for start, end, members in buckets:
+                L = shard_len(end - start, world)
+                assert L % 64 == 0 and L * world >= end - start and L * (world - 1) < end - start + 64 * world
+                for i in members:
+                    cover = np.zeros(sizes[i], np.int32)
+                    for r in range(world):
+                        s0, c = piece_of(start, end - start, offsets[i], sizes[i], r, world)
+                        assert 0 <= s0 and s0 + c <= sizes[i]
+                        if c:
+                            lo = start + r * L
+                            assert lo <= offsets[i] + s0 and offsets[i] + s0 + c <= min(lo + L, end)
+                            assert (offsets[i] + s0) % 64 == 0
+                        cover[s0:s0 + c] += 1
+                    assert (cover == 1).all()
     offsets, total, buckets = plan_arena([10] * 100, 1 << 30, max_members=32)
     assert [len(m) for _, _, m in buckets] == [32, 32, 32, 4]
     assert sorted(i for _, _, m in buckets for i in m) == list(range(100))
