@@ -556,6 +556,7 @@ def run_ours(args, env):
         # replicated weights must still be replicated: one fp32 sum per parameter (the same
         # reduction kernel on every rank), hashed, compared across ranks
         import hashlib
+        ddp.sync_parameters()      # mode p2p with lazy_master: refresh the replicas' fp32 copies first (outside every timed region)
         sums = np.array([float(sk.asnumpy(sk.sum(p._data)).reshape(-1)[0]) for p in params], np.float64)
         digest = hashlib.sha256(sums.tobytes()).hexdigest()[:16]
         digests = rdv.all_gather_str(digest)

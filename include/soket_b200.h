@@ -499,6 +499,7 @@ typedef struct {
 typedef struct {
     double lr, beta1, beta2, eps, weight_decay, one_minus_beta1_t, one_minus_beta2_t, grad_scale, update_bound;
     int share_grads;         /* also leave the reduced gradient (sum over ranks) in every replica's arena */
+    int lazy_master;         /* GEMM weights reach the replicas as hi / lo only; fp32 copies via sk_dp_p2p_gather */
 } sk_p2p_adam;
 /* One bucket = arena elements [bucket_start, bucket_start + bucket_len); rank r owns the piece
  * [bucket_start + r * L, bucket_start + min((r + 1) * L, bucket_len)) with L = sk_p2p_shard_len(bucket_len, world).
@@ -511,6 +512,8 @@ int64_t sk_p2p_shard_len(int64_t bucket_len, int world);
 int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
                      float *staging, int n_tensors, const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper,
                      unsigned int *scratch);
+/* push this rank's piece of the fp32 parameters of a bucket into every replica (current launch stream) */
+int sk_dp_p2p_gather(const sk_p2p_peers *peers, int64_t bucket_start, int64_t bucket_len);
 /* copy-engine probe between two device buffers (either may be a peer mapping from sk_ipc_open): reps x n_copies
  * cudaMemcpyAsync of `bytes` each, round-robin over n_streams streams; *ms = CUDA-event time of the batch */
 int sk_p2p_copy_probe(void *dst, const void *src, size_t bytes, int n_copies, int n_streams, int reps, float *ms);

@@ -26,6 +26,7 @@ def main():
     # DP_WIDE=1: wide enough for the tcgen05 GEMMs / staged LayerNorm kernels of the benchmark
     wide = os.environ.get("DP_WIDE", "0") == "1"
     dim, hidden, nb, C, B = (784, 512, 3, 10, 1024) if wide else (784, 256, 2, 10, 512)
+    B = int(os.environ.get("DP_BATCH", B))     # global rows (>= 256 per rank keeps every Linear on the pre-split GEMM path)
     norm = os.environ.get("DP_NORM", "layer")
     # SGD is linear in the gradient: strict multi-step comparison.  Adam's first steps are
     # lr * g / (|g| + eps): elements whose true gradient is zero (every bias in front of a
@@ -53,7 +54,7 @@ def main():
     # replica's arena so that the gradient check below reads the same thing in both modes
     mode = os.environ.get("DP_MODE", "nccl")
     ddp = dp.DataParallel(opt, rdv, bucket_mb=float(os.environ.get("DP_BUCKET_MB", "0.25")), mode=mode,
-                          share_grads=True)   # several buckets
+                          share_grads=True, lazy_master=os.environ.get("DP_LAZY", "0") == "1")   # several buckets
     ddp.broadcast_parameters(0)
     crit = nn.SoftmaxCrossEntropyLoss()
     oo = O.Adam(len(om.names()), lr=1e-3) if use_adam else O.SGD(len(om.names()), lr=0.05)
@@ -133,6 +134,7 @@ def main():
             for k, v in zip(names, oo.step([om.params[k] for k in names], [acc[k] for k in names])):
                 om.params[k] = v
             assert abs(losses[-1] - shard_losses[0]) <= 1e-4 * max(1.0, abs(shard_losses[0])), (step, losses[-1], shard_losses[0])
+    ddp.sync_parameters()        # lazy_master: the replicas' fp32 copies of the GEMM weights
     if env.rank == 0:
         worst = 0.0
         per = []
@@ -176,7 +178,7 @@ def p2p_matches_nccl_check(env, rdv, start, dim, hidden, nb, C, B):
         for k, t in named.items():
             t.data = soket.Tensor((start[k] if env.rank == 0 else np.full_like(start[k], 3.0)).copy())
         opt = Adam(model.parameters(), lr=1e-3)
-        ddp = dp.DataParallel(opt, rdv, bucket_mb=0.25, mode=mode)
+        ddp = dp.DataParallel(opt, rdv, bucket_mb=0.25, mode=mode, lazy_master=os.environ.get("DP_LAZY", "0") == "1")
         ddp.broadcast_parameters(0)
         crit = nn.SoftmaxCrossEntropyLoss()
         rng = np.random.default_rng(11)
@@ -189,6 +191,7 @@ def p2p_matches_nccl_check(env, rdv, start, dim, hidden, nb, C, B):
             loss.backward()
             ddp.step()
             losses.append(loss.item())
+        ddp.sync_parameters()
         params = {k: t.numpy() for k, t in named.items()}
         digest = repr(float(sum(float(np.abs(v.astype(np.float64)).sum()) for v in params.values())))
         assert len(set(rdv.all_gather_str(digest))) == 1, "replicas diverged in mode " + mode

@@ -299,6 +299,8 @@ cdef extern from "soket_b200.h" nogil:
         double grad_scale
         double update_bound
         int share_grads
+        int lazy_master
+    int sk_dp_p2p_gather(const sk_p2p_peers *peers, int64_t bucket_start, int64_t bucket_len)
     int64_t sk_p2p_shard_len(int64_t bucket_len, int world)
     int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
                          float *staging, int n_tensors, const sk_p2p_tensor *tensors, const sk_p2p_adam *hyper,

@@ -507,7 +507,7 @@ def p2p_shard_len(int64_t bucket_len, int world):
 def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, int64_t bucket_start, int64_t bucket_len,
                   ndarray staging, list tensors, double lr, double beta1, double beta2,
                   double eps, double weight_decay, double one_minus_beta1_t, double one_minus_beta2_t,
-                  double grad_scale, double update_bound, bint share_grads):
+                  double grad_scale, double update_bound, bint share_grads, bint lazy_master=False):
     """One bucket of the peer-memory data-parallel Adam step (sk_dp_p2p_update) on the current launch stream.
     tensors: [(param ndarray, arena offset, start, count, m, v, SplitMat or None, slot, first)] -- start / count =
     the part of the tensor inside this rank's piece of the bucket; staging: world * shard_len float32 (local)."""
@@ -521,6 +521,7 @@ def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, int64_t bucket_
     h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay
     h.one_minus_beta1_t = one_minus_beta1_t; h.one_minus_beta2_t = one_minus_beta2_t
     h.grad_scale = grad_scale; h.update_bound = update_bound; h.share_grads = 1 if share_grads else 0
+    h.lazy_master = 1 if lazy_master else 0
     try:
         for i in range(n):
             p, off, start, count, m, v, split, slot, first = tensors[i]
@@ -543,6 +544,11 @@ def dp_p2p_update(P2pPeers peers, int bucket, unsigned int step, int64_t bucket_
         p._touch()                                       # every replica of p is rewritten by this launch
         if tensors[i][6] is not None:
             _bind_split(<SplitMat> tensors[i][6], p)     # ... and so is its operand split
+
+
+def dp_p2p_gather(P2pPeers peers, int64_t bucket_start, int64_t bucket_len):
+    """Push this rank's piece of a bucket's fp32 parameters into every replica (current launch stream)."""
+    _check(sk_dp_p2p_gather(&peers.c, bucket_start, bucket_len))
 
 
 def dp_p2p_wait(P2pPeers peers, unsigned int step, list bucket_ids):

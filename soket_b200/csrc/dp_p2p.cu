@@ -324,9 +324,10 @@ int sk_ipc_close_all(void) {
 
 // streams and events of the peer-memory update (created on first use)
 struct P2pStreams {
-  cudaStream_t pull = nullptr, push[2] = {nullptr, nullptr}, flag = nullptr;
-  static constexpr int kRing = 64;
-  cudaEvent_t ready[kRing], pulled[kRing], updated[kRing], pushed[kRing][2];
+  static constexpr int kRing = 64, kMax = SK_P2P_MAX_WORLD - 1;
+  cudaStream_t pull[kMax], push[kMax], flag = nullptr;
+  int n_pull = 1, n_push = 2;
+  cudaEvent_t ready[kRing], updated[kRing], pulled[kRing][kMax], pushed[kRing][kMax];
   unsigned int next = 0;
   bool ok = false;
 };
@@ -334,19 +335,27 @@ static P2pStreams g_p2p;
 
 static int p2p_streams_init() {
   if (g_p2p.ok) return SK_OK;
+  // SOKET_B200_P2P_PULL_STREAMS / _PUSH_STREAMS: copies to different peers may run on different copy engines
+  const char *e;
+  if ((e = getenv("SOKET_B200_P2P_PULL_STREAMS"))) g_p2p.n_pull = atoi(e);
+  if ((e = getenv("SOKET_B200_P2P_PUSH_STREAMS"))) g_p2p.n_push = atoi(e);
+  g_p2p.n_pull = g_p2p.n_pull < 1 ? 1 : g_p2p.n_pull > P2pStreams::kMax ? P2pStreams::kMax : g_p2p.n_pull;
+  g_p2p.n_push = g_p2p.n_push < 1 ? 1 : g_p2p.n_push > P2pStreams::kMax ? P2pStreams::kMax : g_p2p.n_push;
   // the transfers must not queue behind compute: highest priority
   int lo = 0, hi = 0;
   SK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.pull, cudaStreamNonBlocking, hi));
-  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.push[0], cudaStreamNonBlocking, hi));
-  SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.push[1], cudaStreamNonBlocking, hi));
+  for (int i = 0; i < P2pStreams::kMax; ++i) {
+    SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.pull[i], cudaStreamNonBlocking, hi));
+    SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.push[i], cudaStreamNonBlocking, hi));
+  }
   SK_CUDA(cudaStreamCreateWithPriority(&g_p2p.flag, cudaStreamNonBlocking, hi));
   for (int i = 0; i < P2pStreams::kRing; ++i) {
     SK_CUDA(cudaEventCreateWithFlags(&g_p2p.ready[i], cudaEventDisableTiming));
-    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pulled[i], cudaEventDisableTiming));
     SK_CUDA(cudaEventCreateWithFlags(&g_p2p.updated[i], cudaEventDisableTiming));
-    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pushed[i][0], cudaEventDisableTiming));
-    SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pushed[i][1], cudaEventDisableTiming));
+    for (int j = 0; j < P2pStreams::kMax; ++j) {
+      SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pulled[i][j], cudaEventDisableTiming));
+      SK_CUDA(cudaEventCreateWithFlags(&g_p2p.pushed[i][j], cudaEventDisableTiming));
+    }
   }
   g_p2p.ok = true;
   return SK_OK;
@@ -432,18 +441,23 @@ int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, i
   // 2. copy engines pull this rank's shard of every peer's gradients into the staging rows
   if (my_len > 0) {
     SK_CUDA(cudaEventRecord(g_p2p.ready[slot], s0));
-    SK_CUDA(cudaStreamWaitEvent(g_p2p.pull, g_p2p.ready[slot], 0));
+    for (int j = 0; j < g_p2p.n_pull; ++j) SK_CUDA(cudaStreamWaitEvent(g_p2p.pull[j], g_p2p.ready[slot], 0));
     for (int k = 1; k < W; ++k) {
       const int q = (R + k) % W;                      // every rank starts with a different peer
       SK_CUDA(cudaMemcpyAsync(staging + (int64_t)q * stride, peers->grads[q] + my_start, (size_t)my_len * 4,
-                              cudaMemcpyDefault, g_p2p.pull));
+                              cudaMemcpyDefault, g_p2p.pull[(k - 1) % g_p2p.n_pull]));
     }
-    SK_CUDA(cudaEventRecord(g_p2p.pulled[slot], g_p2p.pull));
-    SK_CUDA(cudaStreamWaitEvent(s0, g_p2p.pulled[slot], 0));
+    for (int j = 0; j < g_p2p.n_pull; ++j) {
+      SK_CUDA(cudaEventRecord(g_p2p.pulled[slot][j], g_p2p.pull[j]));
+      SK_CUDA(cudaStreamWaitEvent(s0, g_p2p.pulled[slot][j], 0));
+    }
   }
   // 3. the local update: sum in rank order, Adam, operand split, shard maxima to every rank's parts table
   {
     static const int grid_env = getenv("SOKET_B200_P2P_GRID") ? atoi(getenv("SOKET_B200_P2P_GRID")) : 0;
+    // SOKET_B200_P2P_GRID (default two CTAs per SM): the kernel is HBM-bound on a 1/W shard and runs on a
+    // high-priority stream beside backward's GEMMs -- it borrows the SMs briefly (measured at 2 ranks: 74 CTAs
+    // stretch it to 0.5 ms per bucket and the step from 19.7 to 21.2 ms)
     int grid = grid_env > 0 ? grid_env : 2 * ctx().num_sms;
     if (grid > blocks) grid = blocks;
     if (grid < 1) grid = 1;                           // a rank without a shard still publishes (zero) maxima
@@ -452,35 +466,66 @@ int sk_dp_p2p_update(const sk_p2p_peers *peers, int bucket, unsigned int step, i
     p2p_adam_kernel<<<grid, kP2pThreads, 0, s0>>>(a);
     SK_LAUNCH_CHECK();
   }
-  // 4. copy engines push the shard of the new weights (and their split) into every replica; S0 does not wait
+  // 4. copy engines push this rank's piece of the new weights into every replica; S0 does not wait.  A GEMM
+  //    weight travels as its hi / lo operand split (what forward and backward read); its fp32 master copy too
+  //    unless hyper->lazy_master (then sk_dp_p2p_gather refreshes the replicas' fp32 copies on demand)
   SK_CUDA(cudaEventRecord(g_p2p.updated[slot], s0));
-  for (int h = 0; h < 2; ++h) SK_CUDA(cudaStreamWaitEvent(g_p2p.push[h], g_p2p.updated[slot], 0));
+  for (int j = 0; j < g_p2p.n_push; ++j) SK_CUDA(cudaStreamWaitEvent(g_p2p.push[j], g_p2p.updated[slot], 0));
   if (my_len > 0) {
     for (int k = 1; k < W; ++k) {
       const int q = (R + k) % W;
-      cudaStream_t ps = g_p2p.push[k & 1];
-      SK_CUDA(cudaMemcpyAsync(peers->params[q] + my_start, peers->params[R] + my_start, (size_t)my_len * 4,
-                              cudaMemcpyDefault, ps));
-      if (any_split) {
-        SK_CUDA(cudaMemcpyAsync((__half *)peers->hi[q] + my_start, (const __half *)peers->hi[R] + my_start,
-                                (size_t)my_len * 2, cudaMemcpyDefault, ps));
-        SK_CUDA(cudaMemcpyAsync((__half *)peers->lo[q] + my_start, (const __half *)peers->lo[R] + my_start,
-                                (size_t)my_len * 2, cudaMemcpyDefault, ps));
+      cudaStream_t ps = g_p2p.push[(k - 1) % g_p2p.n_push];
+      if (!hyper->lazy_master) {
+        SK_CUDA(cudaMemcpyAsync(peers->params[q] + my_start, peers->params[R] + my_start, (size_t)my_len * 4,
+                                cudaMemcpyDefault, ps));
+      }
+      for (int i = 0; i < n_tensors; ++i) {
+        const sk_p2p_tensor &t = tensors[i];
+        if (t.count == 0) continue;
+        const int64_t e = t.offset + t.start;
+        if (t.scale4) {
+          SK_CUDA(cudaMemcpyAsync((__half *)peers->hi[q] + e, (const __half *)peers->hi[R] + e, (size_t)t.count * 2,
+                                  cudaMemcpyDefault, ps));
+          SK_CUDA(cudaMemcpyAsync((__half *)peers->lo[q] + e, (const __half *)peers->lo[R] + e, (size_t)t.count * 2,
+                                  cudaMemcpyDefault, ps));
+        } else if (hyper->lazy_master) {
+          SK_CUDA(cudaMemcpyAsync(peers->params[q] + e, peers->params[R] + e, (size_t)t.count * 4, cudaMemcpyDefault, ps));
+        }
       }
       if (a.share_grads)
         SK_CUDA(cudaMemcpyAsync(peers->grads[q] + my_start, peers->grads[R] + my_start, (size_t)my_len * 4,
                                 cudaMemcpyDefault, ps));
     }
   }
-  // 5. done[bucket][me] on every rank once both push streams have drained
-  for (int h = 0; h < 2; ++h) {
-    SK_CUDA(cudaEventRecord(g_p2p.pushed[slot][h], g_p2p.push[h]));
-    SK_CUDA(cudaStreamWaitEvent(g_p2p.flag, g_p2p.pushed[slot][h], 0));
+  // 5. done[bucket][me] on every rank once the push streams have drained
+  for (int j = 0; j < g_p2p.n_push; ++j) {
+    SK_CUDA(cudaEventRecord(g_p2p.pushed[slot][j], g_p2p.push[j]));
+    SK_CUDA(cudaStreamWaitEvent(g_p2p.flag, g_p2p.pushed[slot][j], 0));
   }
   P2pReadyArgs d = r;
   d.ready_off = done_off;
   p2p_done_kernel<<<1, 32, 0, g_p2p.flag>>>(d);
   SK_LAUNCH_CHECK();
+  return SK_OK;
+}
+
+// the fp32 master copy of this rank's piece of a bucket into every replica (lazy_master: before anything reads
+// the parameters as fp32 -- a checkpoint, a checksum, p.numpy()); on the current launch stream
+int sk_dp_p2p_gather(const sk_p2p_peers *peers, int64_t bucket_start, int64_t bucket_len) {
+  int rc;
+  if ((rc = ensure_init())) return rc;
+  SK_REQUIRE(peers && peers->world >= 2 && peers->world <= SK_P2P_MAX_WORLD && bucket_start >= 0 && bucket_len > 0,
+             "sk_dp_p2p_gather: bad argument");
+  const int W = peers->world, R = peers->rank;
+  const int64_t stride = sk_p2p_shard_len(bucket_len, W);
+  const int64_t my_start = bucket_start + (int64_t)R * stride;
+  int64_t my_len = bucket_start + bucket_len - my_start;
+  if (my_len > stride) my_len = stride;
+  for (int k = 1; k < W && my_len > 0; ++k) {
+    const int q = (R + k) % W;
+    SK_CUDA(cudaMemcpyAsync(peers->params[q] + my_start, peers->params[R] + my_start, (size_t)my_len * 4,
+                            cudaMemcpyDefault, stream()));
+  }
   return SK_OK;
 }
 

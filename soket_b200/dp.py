@@ -239,7 +239,7 @@ class DataParallel:
     optimizer kernel)."""
 
     def __init__(self, optim, rdv: Rendezvous | None, overlap: bool = True, bucket_mb: float | None = None,
-                 mode: str | None = None, share_grads: bool | None = None):
+                 mode: str | None = None, share_grads: bool | None = None, lazy_master: bool | None = None):
         from soket_b200 import _core as B
         from soket_b200 import _fused as F
         from soket_b200 import engine as E
@@ -278,6 +278,12 @@ class DataParallel:
         if share_grads is None:
             share_grads = os.environ.get("SOKET_B200_DP_SHARE_GRADS", "0") == "1"
         self.share_grads = bool(share_grads)
+        # mode 'p2p': GEMM weights reach the other replicas as their fp16 hi / lo operand split only (what forward
+        # and backward read); a replica's fp32 copy of a weight is current on its owner's piece only until
+        # `sync_parameters()` (called by `close()`) -- halves the bytes pushed over NVLink per step
+        if lazy_master is None:
+            lazy_master = os.environ.get("SOKET_B200_DP_LAZY_MASTER", "0") == "1"
+        self.lazy_master = bool(lazy_master) and mode == "p2p"
         offsets, total, buckets = plan_arena([int(p.size) for p in params], int(bucket_mb * (1 << 20) / 4),
                                              max_members=32 if mode == "p2p" else None)
         self._offsets, self._total = offsets, total
@@ -440,7 +446,7 @@ class DataParallel:
         try:
             F.dp_p2p_update(self._peers, b.index, self._step, b.start, b.end - b.start, self._staging, tensors, o._lr, o._beta1, o._beta2, o._eps,
                             o._weight_decay if o._have_weight_decay else 0.0, o._one_minus_beta1_t, o._one_minus_beta2_t,
-                            1.0 / self.world, ub, self.share_grads)
+                            1.0 / self.world, ub, self.share_grads, self.lazy_master)
         finally:
             B.launch_stream(B.STREAM_COMPUTE)
         b.ev_reduced.record(B.STREAM_OPT)            # this rank's shard of the bucket is updated and published
@@ -531,6 +537,18 @@ class DataParallel:
         recorded on the comm / optimizer streams by the most recent `step()`; for phase timing."""
         return (self._last_bucket.ev_reduced if self._last_bucket is not None else None), self._ev_done
 
+    def sync_parameters(self):
+        """Collective (every rank calls it, between steps): after it every replica's fp32 parameters are current.
+        A no-op unless mode 'p2p' runs with lazy_master."""
+        if self.world == 1 or not self.lazy_master or self._closed:
+            return
+        self.B.synchronize()
+        self.rdv.barrier()                           # nobody is still inside a step
+        for b in self._buckets:
+            self.F.dp_p2p_gather(self._peers, b.start, b.end - b.start)
+        self.B.synchronize()
+        self.rdv.barrier()
+
     def bucket_times(self, origin):
         """[(MB, ms from `origin` until the bucket's gradients were complete, ms until its all-reduce had
         finished)] of the most recent step, in launch order (call after the step has drained)."""
@@ -549,6 +567,7 @@ class DataParallel:
 
     def close(self):
         if self.world > 1 and not self._closed:
+            self.sync_parameters()
             self._closed = True
             self.E.set_leaf_grad_hook(None)
             for p in self.optim._params:

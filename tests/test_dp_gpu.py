@@ -15,15 +15,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("norm,opt,wide,mode", [("layer", "sgd", 0, "nccl"), ("batch", "sgd", 0, "nccl"),
                                                 ("layer", "adam", 0, "nccl"), ("layer", "sgd", 1, "nccl"),
                                                 ("layer", "adam", 1, "nccl"), ("layer", "adam", 0, "p2p"),
-                                                ("layer", "adam", 1, "p2p"), ("batch", "adam", 0, "p2p")])
+                                                ("layer", "adam", 1, "p2p"), ("batch", "adam", 0, "p2p"),
+                                                ("layer", "adam", 1, "p2p-lazy")])
 def test_two_rank_training_matches_shard_emulation(sk, norm, opt, wide, mode):
     """mode nccl: ncclAllReduce per gradient bucket + replicated optimizer; mode p2p: one peer-memory kernel per
     bucket (reduce-scatter + Adam on the shard + operand split + all-gather, csrc/dp_p2p.cu), which is also
     compared with the nccl mode over six free-running steps (bit-identical at 2 ranks)."""
     if sk.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt, DP_WIDE=str(wide), DP_MODE=mode)
-    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam") + 7 * wide + 13 * (mode == "p2p")
+    lazy = mode.endswith("-lazy")       # GEMM weights travel as hi / lo only; fp32 replicas refreshed by sync_parameters()
+    mode = mode.split("-")[0]
+    env = dict(os.environ, DP_NORM=norm, DP_OPT=opt, DP_WIDE=str(wide), DP_MODE=mode, DP_LAZY="1" if lazy else "0")
+    port = 29610 + 40 * ["layer", "batch"].index(norm) + 80 * (opt == "adam") + 7 * wide + 13 * (mode == "p2p") + 3 * lazy
     r = subprocess.run(
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
          "--master-addr", "127.0.0.1", "--master-port", str(port),
