@@ -235,17 +235,18 @@ int sk_init(int device) {
   SK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   {
     // the collective and the per-bucket optimizer update run BESIDE backward's persistent GEMMs, which hold
-    // every SM for a whole kernel: at each kernel boundary the pending CTAs of the higher-priority stream are
+    // every SM for a whole kernel: at each kernel boundary the pending CTAs of a higher-priority stream are
     // placed first, so a bucket's all-reduce / update starts after at most one GEMM instead of queueing behind
-    // several.  Measured (strong scaling, 8192 rows over W ranks): at W = 2 (350 us GEMMs) the time from
-    // "gradients complete" to "bucket reduced" drops from 1.2 to 0.35 ms and the step from 21.6 to 20.7 ms;
-    // at W = 8 (100 us GEMMs) there is no queueing to remove and the earlier NCCL CTAs cost 2.7 % (9.43 ->
-    // 9.68 ms).  Default: on below 8 ranks (WORLD_SIZE as the launcher exports it); SOKET_B200_STREAM_PRIORITY
-    // = 0 / 1 overrides.
+    // several.  Measured (strong scaling, 8192 rows over W ranks, profiles/r2_dp_scaling.md): at W = 2 (350 us
+    // GEMMs) the time from "gradients complete" to "bucket reduced" drops from 1.2 to 0.35 ms and the step by
+    // ~2 % (20.7 / 21.2 vs 21.3 / 21.6 ms); at W = 4 nothing changes (12.72 vs 12.66 ms); at W = 8 (100 us
+    // GEMMs) there is no queueing to remove and the earlier NCCL CTAs cost 2.7 % (9.68 vs 9.43 ms).
+    // Default: on up to 2 ranks (WORLD_SIZE as the launcher exports it); SOKET_B200_STREAM_PRIORITY = 0 / 1
+    // overrides.
     int lo = 0, hi = 0;
     SK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     const char *ws = getenv("WORLD_SIZE");
-    bool prio = !ws || atoi(ws) < 8;
+    bool prio = !ws || atoi(ws) <= 2;
     if (getenv("SOKET_B200_STREAM_PRIORITY")) prio = atoi(getenv("SOKET_B200_STREAM_PRIORITY")) != 0;
     const int p = prio ? hi : 0;
     SK_CUDA(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, p));
