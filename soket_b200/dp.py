@@ -26,6 +26,14 @@ Updating a layer's parameters while backward is still running is safe: every ker
 that reads them in this step (the layer's own forward and backward) was queued on the
 compute stream before the event its bucket waits for.
 
+Mode 'p2p' (opt-in: `DataParallel(mode="p2p")` / SOKET_B200_DP_MODE=p2p; Adam) replaces the
+all-reduce + replicated update of a bucket by reduce-scatter + sharded Adam + all-gather over
+CUDA-IPC peer memory: the copy engines pull this rank's piece of every peer's gradients, one
+local kernel sums them in rank order, applies Adam to 1/W of the state and emits the GEMM
+weights' fp16 hi / lo operand split, the copy engines push the piece into every replica's
+arenas; ready / done flags in peer memory order it (csrc/dp_p2p.cu).
+Measured: +5.5 % over the NCCL mode at 2 ranks, slower at 8 (profiles/r2_dp_scaling.md).
+
 Rendezvous: ranks come from the environment torchrun sets (RANK, LOCAL_RANK,
 WORLD_SIZE, MASTER_ADDR, MASTER_PORT).  The 128-byte NCCL unique id goes from rank 0 to the
 others through a file under /dev/shm (class Rendezvous), as do host-side barriers and the few
@@ -457,10 +465,6 @@ class DataParallel:
 
     def _peers_param_ptr(self, i):
         return self._parena.data_ptr + 4 * self._offsets[i]
-
-    def gather_info(self):
-        """What the peer-memory mode holds where (for reports)."""
-        return {"mode": self.mode, "buckets": len(self._buckets), "share_grads": getattr(self, "share_grads", False)}
 
     def _launch(self, b):
         """Queue the bucket's all-reduce (comm stream) and its optimizer update (optimizer stream)."""
