@@ -299,11 +299,14 @@ def run_reference(args, env):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": ref.cores, "kind": ref.kind,
                          "blas_threads": blas_threads(), "rows_per_step": sample,
                          "env": {k: os.environ.get(k) for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS")},
-                         "sample": f"{args.steps} Adam step(s) of the same model on {sample} rows per step after "
-                                   f"{args.warmup} warm-up step(s) (the full batch is {args.global_batch} rows: "
-                                   f"--cpu-sample-batch {args.global_batch} --steps 3 times it whole; the per-step Adam "
-                                   f"update over 272 M parameters does not shrink with the sample, so full-batch CPU "
-                                   f"throughput is ~15 % higher than this sample's); NumPy/OpenBLAS on all host cores"},
+                         "sample": (f"{args.steps} Adam step(s) of the same model on the WHOLE {sample}-row batch per step "
+                                    f"after {args.warmup} warm-up step(s); NumPy/OpenBLAS on all host cores"
+                                    if sample >= args.global_batch else
+                                    f"{args.steps} Adam step(s) of the same model on {sample} rows per step after "
+                                    f"{args.warmup} warm-up step(s) (the full batch is {args.global_batch} rows: "
+                                    f"--cpu-sample-batch {args.global_batch} --steps 3 times it whole; the per-step Adam "
+                                    f"update over 272 M parameters does not shrink with the sample, so full-batch CPU "
+                                    f"throughput is ~15 % higher than this sample's); NumPy/OpenBLAS on all host cores")},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
